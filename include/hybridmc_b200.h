@@ -1,0 +1,251 @@
+/*
+ * hybridmc_b200.h — C-ABI of the B200-native HybridMC ensemble engine.
+ *
+ * This is the drop-in boundary for the reference's hot path: everything the
+ * reference executes inside run_trajectory / run_trajectory_eq / wang_landau
+ * (/root/reference/src/main.cc:151-305) and the functions those call
+ * (src/hardspheres.cc, src/crankshaft.cc, src/entropy.cc).  The host program
+ * (C++17 `hybridmc` executable, or the ctypes mirror in hybridmc_b200/) calls
+ * these entry points once per phase / iteration batch — never per event.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns 0 on success, <0 on error; the message for the
+ *     last error on a handle is hmc_last_error(h) (hmc_last_error(NULL) for
+ *     hmc_create failures).  No exception crosses the boundary.
+ *   - the caller owns all host buffers; the library owns device memory.
+ *   - one handle per device; a handle is not thread-safe, distinct handles are.
+ *   - all work is ordered on the handle's CUDA stream; getters synchronise.
+ *   - there is NO CPU fallback: without a CUDA device hmc_create fails.
+ *
+ * Ensemble layout: a handle holds T "transitions" (one hmc_params each; all
+ * share nbeads / box / cell geometry) times R replicas per transition.
+ * Replica index r in [0, T*R) belongs to transition r / R.
+ */
+#ifndef HYBRIDMC_B200_H
+#define HYBRIDMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMC_MAX_BONDS 64 /* Config is a uint64 bitmask (src/config.h:18) */
+#define HMC_MAX_BEADS 64
+#define HMC_MAX_SEEDS 8
+
+/* POD copy of the reference's Param (src/params.h:10-101) with the bond lists
+ * of NonlocalBonds (src/config.h:21-56) flattened.  Field meaning and JSON key
+ * are identical to from_json(Param) (src/main.cc:500-562); squares (rh2, ...)
+ * are derived inside the library exactly as there (x*x). */
+typedef struct hmc_params {
+  double m;         /* "m" */
+  double sigma;     /* "sigma_bb" */
+  double near_min, near_max;   /* nearest-neighbour well */
+  double nnear_min, nnear_max; /* next-nearest well */
+  double rh, rc;               /* nonlocal hard core / bond radius */
+  double stair;                /* valid iff has_stair */
+  double p_rc;                 /* valid iff has_p_rc */
+  double length;               /* box length */
+  double del_t, del_t_wl;
+  double gamma, gamma_f;
+  double temp;
+  double pos_scale, neg_scale, sig_level;
+  uint64_t tries;
+  uint32_t has_stair, has_p_rc;
+  uint32_t nbeads, ncell;
+  uint32_t nsteps, nsteps_eq, nsteps_wl, write_step;
+  uint32_t mc_moves, mc_write;
+  uint32_t total_iter, total_iter_eq;
+  uint32_t max_g_test_count, max_nbonds;
+  uint32_t n_nonlocal, n_transient, n_permanent, n_seeds;
+  uint32_t nonlocal_bonds[HMC_MAX_BONDS][2];
+  uint32_t transient_bonds[HMC_MAX_BONDS][2];
+  uint32_t permanent_bonds[HMC_MAX_BONDS][2];
+  uint32_t seeds[HMC_MAX_SEEDS];
+} hmc_params;
+
+/* Event types = index in the reference's Event variant (src/event.h:99-102). */
+enum hmc_event_type {
+  HMC_EV_MIN_NEAREST = 0,
+  HMC_EV_MAX_NEAREST = 1,
+  HMC_EV_MIN_NNEAREST = 2,
+  HMC_EV_MAX_NNEAREST = 3,
+  HMC_EV_MIN_NONLOCAL_INNER = 4,
+  HMC_EV_MAX_NONLOCAL_INNER = 5,
+  HMC_EV_MAX_NONLOCAL_OUTER = 6,
+  HMC_EV_BEAD_CELL = 7
+};
+
+/* One valid (processed) event; for HMC_EV_BEAD_CELL j is the wall
+ * (CellEvent::Wall, src/event.h:86: xpos,xneg,ypos,yneg,zpos,zneg). */
+typedef struct hmc_event {
+  double t;
+  uint32_t type;
+  uint32_t i, j;
+  uint32_t pad;
+} hmc_event;
+
+/* Phases of the reference's main (src/main.cc:411-491). */
+enum hmc_phase {
+  HMC_PHASE_EQ = 0,  /* run_trajectory_eq   main.cc:151-169 (nsteps_eq, no MC, no sampling) */
+  HMC_PHASE_WL = 1,  /* run_trajectory_wl   main.cc:249-305 (nsteps_wl, del_t_wl, ±gamma) */
+  HMC_PHASE_MAIN = 2 /* run_trajectory      main.cc:171-247 (sampling + crankshaft) */
+};
+
+/* Per-replica error flags (sticky; reference throws / asserts at these points). */
+enum hmc_error_flag {
+  HMC_ERR_LOCAL_OVERLAP = 1,    /* main.cc:48-51 "local beads overlap" */
+  HMC_ERR_NONLOCAL_OVERLAP = 2, /* main.cc:53-56 "nonlocal beads overlap" */
+  HMC_ERR_ENERGY = 4,           /* main.cc:219-225 "energy is not conserved" */
+  HMC_ERR_NAN = 8,              /* non-finite event time */
+  HMC_ERR_TAPE_UNDERRUN = 16,   /* injected crankshaft tape exhausted */
+  HMC_ERR_SAMPLE_OVERFLOW = 32  /* optional sample buffer full (samples dropped) */
+};
+
+typedef struct hmc_engine *hmc_handle;
+
+/* ---- lifecycle --------------------------------------------------------- */
+
+/* Build an ensemble on CUDA device `device`: n_transitions parameter sets
+ * (same nbeads/length/ncell), replicas_per_transition replicas each.
+ * Validates what initialize_system validates (ncell >= 4, lcell >= rc or
+ * stair; main.cc:58-69) and from_json's stair check (main.cc:535-537).
+ * Replaces: Param construction + System/Box/Cells/EventQueue set-up
+ * (main.cc:362-380, 187-190). */
+int hmc_create(const hmc_params *transitions, int n_transitions,
+               int replicas_per_transition, int device, hmc_handle *out);
+int hmc_destroy(hmc_handle h);
+const char *hmc_last_error(hmc_handle h);
+/* ABI version of this header (bumped on any signature change). */
+int hmc_abi_version(void);
+
+/* ---- state in / out ------------------------------------------------------ */
+
+/* pos[R_total][nbeads][3], unwrapped coordinates as in System::pos
+ * (src/system.h:15).  Replaces init_pos / read_input results (main.cc:26-43). */
+int hmc_set_positions(hmc_handle h, const double *pos);
+int hmc_get_positions(hmc_handle h, double *pos);
+int hmc_get_velocities(hmc_handle h, double *vel);
+/* config[R_total]: bond bitmask per replica (UpdateConfig::config). */
+int hmc_set_config(hmc_handle h, const uint64_t *config);
+int hmc_get_config(hmc_handle h, uint64_t *config);
+/* Recompute every replica's bitmask from its positions:
+ * init_update_config (src/hardspheres.cc:144-171). */
+int hmc_init_config_from_positions(hmc_handle h);
+/* s_bias[n_transitions][nstates] broadcast to the replicas of each transition
+ * (System::s_bias; init_s src/entropy.cc:14-20 gives the starting values). */
+int hmc_set_s_bias(hmc_handle h, const double *s_bias, int nstates);
+/* s_bias[R_total][nstates]: per replica (they differ after the WL phase). */
+int hmc_get_s_bias(hmc_handle h, double *s_bias, int nstates);
+/* Zero bead clocks and collision counters and the step index
+ * (main.cc:414-419, 436-439, 452-457). */
+int hmc_reset_clocks(hmc_handle h);
+/* Zero config_count and the sample cursors (main.cc:459-461). */
+int hmc_reset_counts(hmc_handle h);
+
+/* ---- production path: device Philox4x32-10 RNG ------------------------- */
+
+/* Philox key; replica r uses counter word 3 = r. */
+int hmc_seed(hmc_handle h, uint32_t seed0, uint32_t seed1);
+/* Run n_iters iterations of `phase` for every replica, starting at iteration
+ * index first_iter (the reference's `iter` / `iter_wl`):
+ *   EQ   : n_iters x nsteps_eq MD steps                     (main.cc:428-431)
+ *   WL   : n_iters outer WL iterations (nstates trajectories each, gamma
+ *          schedule of main.cc:283-304, per-replica s_bias[native])
+ *   MAIN : n_iters x (nsteps MD steps + mc_moves crankshafts), sampling
+ *          config_count / dist / config_int                   (main.cc:463-468)
+ * Asynchronous on the handle's stream. */
+int hmc_run(hmc_handle h, int phase, unsigned first_iter, unsigned n_iters);
+int hmc_sync(hmc_handle h);
+
+/* ---- reference-exact path: host-injected RNG stream ---------------------- */
+
+/* Run `nsteps` MD steps (step indices first_step..first_step+nsteps-1,
+ * step_time = step*del_t as in run_step, main.cc:104) with the Maxwell-
+ * Boltzmann draws supplied by the host: normals[R_total][nsteps][nbeads][3]
+ * are the values init_vel assigns BEFORE the centre-of-mass shift
+ * (src/hardspheres.cc:205-209).  phase selects del_t/del_t_wl and sampling;
+ * for WL each "step" is one run_trajectory_wl call (trajectory index
+ * first_step + k, i.e. outer iteration (first_step+k)/nstates) including the
+ * ±gamma update. */
+int hmc_md_steps_injected(hmc_handle h, int phase, unsigned first_step,
+                          unsigned nsteps, const double *normals);
+/* Run n_moves crankshaft moves per replica (src/crankshaft.cc:224-262) from a
+ * raw 32-bit word tape: words[R_total][n_words] are successive outputs of the
+ * host's std::mt19937; sin_tab/cos_tab[R_total][n_words] hold sin/cos of the
+ * angle that libstdc++'s uniform_real_distribution(0,2pi) would form from
+ * words[c], words[c+1] (host libm, so the rotation matrix is bit-identical to
+ * the reference's).  consumed[R_total] returns the words each replica used.
+ * move_offset = index of the first move within the iteration (for the
+ * mc_write bookkeeping of main.cc:232-236). */
+int hmc_crankshaft_injected(hmc_handle h, unsigned move_offset, unsigned n_moves,
+                            const uint32_t *words, const double *sin_tab,
+                            const double *cos_tab, unsigned n_words,
+                            uint32_t *consumed);
+
+/* ---- results ------------------------------------------------------------- */
+
+/* config_count[n_transitions][nstates] (pooled over replicas; only MD-step
+ * samples, main.cc:204,471-473), formed/broken[n_transitions] (CountBond),
+ * err_flags[R_total].  Any pointer may be NULL. */
+int hmc_get_counts(hmc_handle h, uint64_t *config_count, int nstates,
+                   uint64_t *formed, uint64_t *broken, uint32_t *err_flags);
+/* Device pointer of the u64 block [n_transitions][nstates] ++ formed[T] ++
+ * broken[T] ++ events[4] for an in-place NCCL all-reduce by the caller
+ * (torch.distributed / ncclAllReduce); *n_u64 = its length. */
+int hmc_counts_device_ptr(hmc_handle h, void **dptr, uint64_t *n_u64);
+/* events[0] valid collision events (types 0-6), [1] cell crossings,
+ * [2] crankshaft attempts, [3] crankshaft accepted — summed over replicas. */
+int hmc_get_event_counts(hmc_handle h, uint64_t events[4]);
+
+/* Optional per-replica sample buffers (off by default).  rows_per_replica
+ * bounds the dist rows / config_int entries kept per replica between
+ * hmc_reset_counts calls. */
+int hmc_enable_samples(hmc_handle h, unsigned dist_rows_per_replica,
+                       unsigned config_int_per_replica);
+/* dist[R_total][rows][n_nonlocal] (dist_between_nonlocal_beads,
+ * src/hardspheres.cc:1084-1104, one row per MD step), n_rows[R_total]. */
+int hmc_get_dist(hmc_handle h, double *dist, uint32_t *n_rows);
+/* config_int[R_total][cap] in the reference's append order (MD samples and
+ * crankshaft samples interleaved, main.cc:205,234), n[R_total]. */
+int hmc_get_config_int(hmc_handle h, uint64_t *config_int, uint32_t *n);
+/* Fine histogram of every nonlocal-bond distance, pooled per transition:
+ * hist[n_transitions][n_nonlocal][nbins] over [0, rmax). */
+int hmc_enable_dist_hist(hmc_handle h, unsigned nbins, double rmax);
+int hmc_get_dist_hist(hmc_handle h, uint64_t *hist);
+/* First recorded configuration with config == 1 per replica
+ * (unique_config/{pos,vel}, main.cc:211-216): pos/vel[R_total][nbeads][3],
+ * found[R_total]. */
+int hmc_get_unique_config(hmc_handle h, double *pos, double *vel, uint8_t *found);
+
+/* Event trace of one replica (parity / debugging): the next hmc_run /
+ * hmc_md_steps_injected calls append every valid event of `replica` until
+ * `capacity` is reached.  capacity 0 disables. */
+int hmc_enable_trace(hmc_handle h, int replica, unsigned capacity);
+int hmc_get_trace(hmc_handle h, hmc_event *out, unsigned max_events,
+                  unsigned *n_events);
+
+/* ---- entropy update (host-side, tiny) ------------------------------------ */
+
+/* compute_entropy (src/entropy.cc:36-69) on pooled counts, in place. */
+int hmc_compute_entropy(const uint64_t *config_count, double *s_bias, int nstates,
+                        double pos_scale, double neg_scale);
+/* compute_g_val (src/entropy.cc:72-89). */
+double hmc_compute_g_val(const uint64_t *config_count, int nstates);
+/* g_test (src/entropy.cc:92-116): returns 1 accepted, 0 rejected; g_val,
+ * g_crit, p_val optional outputs. */
+int hmc_g_test(const uint64_t *config_count, int nstates, double sig_level,
+               double *g_val, double *g_crit, double *p_val);
+
+/* ---- launch statistics (for bench.py) ------------------------------------ */
+
+/* kernels launched by this handle so far, and the device time (ms, CUDA
+ * events on the handle's stream) of the last hmc_run / injected call. */
+int hmc_get_launch_stats(hmc_handle h, uint64_t *n_launches, float *last_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYBRIDMC_B200_H */
