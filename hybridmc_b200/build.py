@@ -1,0 +1,64 @@
+"""In-tree build of the CUDA library (sm_100a only).
+
+`build_library()` compiles hybridmc_b200/csrc/*.cu with nvcc into
+hybridmc_b200/libhybridmc_b200.so.  Flags that matter:
+  -gencode arch=compute_100a,code=sm_100a   Blackwell B200 only, no PTX fallback
+  -fmad=false                               no FMA contraction: the event times must
+                                            be bit-identical to the reference's
+                                            non-fused x86-64 arithmetic
+  -lineinfo                                 ncu source page maps to the .cu
+  -l:libstdc++.so.6                         this image would otherwise link libstdc++
+                                            statically, which clashes with torch's
+                                            shared copy inside one Python process
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libhybridmc_b200.so")
+SOURCES = ["hmc_kernels.cu", "hmc_api.cu"]
+HEADERS = [os.path.join(CSRC, "hmc_internal.h"),
+           os.path.join(os.path.dirname(HERE), "include", "hybridmc_b200.h")]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; the engine cannot be built (there is no CPU fallback)")
+
+
+def nvcc_flags(extra=()):
+    return ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
+            "-std=c++17", "-Xcompiler", "-fPIC", *extra]
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force=False, verbose=False):
+    if not force and not is_stale():
+        return LIB
+    cmd = [nvcc_path(), *nvcc_flags(), "-shared", "-o", LIB,
+           *[os.path.join(CSRC, s) for s in SOURCES],
+           "-cudart", "static", "-Xlinker", "-l:libstdc++.so.6"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

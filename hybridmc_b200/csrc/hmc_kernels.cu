@@ -1,0 +1,1148 @@
+// hmc_kernels.cu — sm_100a FP64 ensemble kernel for HybridMC's event-driven hybrid
+// Monte Carlo (reference hot path: src/main.cc:45-305 and the hardspheres.cc /
+// crankshaft.cc functions it calls).
+//
+// Design (B200-first, not a translation of the reference's heap + cell lists):
+//   * one GROUP of G lanes (G = 8, 16 or 32, a sub-warp) owns one replica for the
+//     whole launch; groups pull replicas from a global work counter, so there is no
+//     per-step barrier between replicas (event counts per step vary by 10-70 %).
+//   * the replica lives in shared memory as SoA bead arrays (x,y,z,vx,vy,vz,clock),
+//     per-bead 3-D cell indices and an EVENT TABLE with one slot per bead (its next
+//     cell crossing) and one slot per bead pair (its next predicted collision, with
+//     the event type latched at prediction time).  It replaces the reference's
+//     std::priority_queue + per-bead collision counters (src/event.h:15-116):
+//       - executing a collision (i,j) rewrites every slot touching i or j  (= the
+//         counter bump that invalidates queued events, hardspheres.cc:1118-1119)
+//       - executing a cell crossing of i only min-merges predictions for the beads
+//         in the 9 newly adjacent cells and replaces i's cell slot; all other slots
+//         touching i are kept (no counter bump, hardspheres.cc:1622-1645)
+//       - the next event is a lane-parallel argmin over the table + shuffle reduce.
+//     SURVEY.md §7a shows this is bit-identical to the heap; it does none of the
+//     87-90 % stale-pop work of the reference.
+//   * predictions are made exactly when and for whom the reference makes them
+//     (27-cell neighbourhood at a collision, 9 new cells at a crossing; with
+//     ncell >= 4 cell adjacency is a per-pair predicate on the cell indices, so no
+//     per-cell lists are needed), lane-parallel over partner beads.
+//   * all FP64 arithmetic keeps the reference's IEEE operation order; the file is
+//     compiled with -fmad=false so nothing is contracted into FMAs, and uses IEEE
+//     sqrt / division and round-half-away (round()), so event times are
+//     bit-identical to the CPU reference.
+//   * per-replica counter-based Philox4x32-10 RNG (production) or a host-injected
+//     stream (reference-exact mode).
+// No tensor cores: nothing here is a dense contraction.
+#include "hmc_internal.h"
+
+#include <math_constants.h>
+
+namespace {
+
+// ----------------------------------------------------------------- helpers --
+
+struct Smem {
+  double *x, *y, *z, *vx, *vy, *vz, *tm, *evt;
+  uint8_t *evty, *cx, *cy, *cz;
+};
+
+__device__ __forceinline__ Smem carve(unsigned char *base, int nb, int nslots) {
+  Smem s;
+  double *d = reinterpret_cast<double *>(base);
+  s.x = d;
+  s.y = d + nb;
+  s.z = d + 2 * nb;
+  s.vx = d + 3 * nb;
+  s.vy = d + 4 * nb;
+  s.vz = d + 5 * nb;
+  s.tm = d + 6 * nb;
+  s.evt = d + 7 * nb;
+  uint8_t *b = reinterpret_cast<uint8_t *>(d + 7 * nb + nslots);
+  s.evty = b;
+  s.cx = b + nslots;
+  s.cy = s.cx + nb;
+  s.cz = s.cy + nb;
+  return s;
+}
+
+// per-replica register state (uniform across the lanes of a group)
+struct Rep {
+  int r;                 // replica index
+  unsigned long long config;
+  const TransDev *tr;
+  const uint8_t *pinfo;  // pairinfo row of this replica's transition
+  double *sb;            // s_bias of this replica (global)
+  double rc2, stair2, p_rc2;
+  unsigned has_stair, has_p_rc, max_nbonds;
+  unsigned err;
+  unsigned long long n_coll, n_cell, n_att, n_acc, formed, broken;
+  bool tracing;
+};
+
+template <int G> __device__ __forceinline__ unsigned group_mask() {
+  if constexpr (G == 32) {
+    return 0xffffffffu;
+  } else {
+    const unsigned lane = threadIdx.x & 31u;
+    return ((1u << G) - 1u) << (lane & ~unsigned(G - 1));
+  }
+}
+
+__device__ __forceinline__ int pair_index(int i, int j, int nb) {
+  return i * (2 * nb - i - 1) / 2 + (j - i - 1);
+}
+
+// Box::mindist, box.h:22-26
+__device__ __forceinline__ void mindist3(const KArgs &a, double &dx, double &dy, double &dz) {
+  dx -= round(dx * a.inv_l) * a.l;
+  dy -= round(dy * a.inv_l) * a.l;
+  dz -= round(dz * a.inv_l) * a.l;
+}
+
+struct Quad {
+  double t, rv, vv, rr, rv2;
+};
+
+// t_until_inner_coll, hardspheres.cc:217-240
+__device__ __forceinline__ bool inner_time(const Quad &q, double s2, double &tout) {
+  if (!(q.rv < 0)) return false;
+  const double rad1 = q.vv * (q.rr - s2);
+  if (!(q.rv2 > rad1)) return false;
+  tout = q.t + (-q.rv - sqrt(q.rv2 - rad1)) / q.vv;
+  return true;
+}
+// t_until_outer_coll, hardspheres.cc:244-254
+__device__ __forceinline__ double outer_time(const Quad &q, double s2) {
+  const double rad1 = q.vv * (q.rr - s2);
+  return q.t + (-q.rv + sqrt(q.rv2 - rad1)) / q.vv;
+}
+
+struct Bead {
+  double x, y, z, vx, vy, vz, t;
+};
+
+__device__ __forceinline__ Bead load_bead(const Smem &s, int k) {
+  Bead b;
+  b.x = s.x[k];
+  b.y = s.y[k];
+  b.z = s.z[k];
+  b.vx = s.vx[k];
+  b.vy = s.vy[k];
+  b.vz = s.vz[k];
+  b.t = s.tm[k];
+  return b;
+}
+
+// delta_tpv (hardspheres.cc:372-392) for the ordered pair lo<hi, followed by the
+// type logic of if_nearest_bond / if_nnearest_bond (:863-923) or if_coll (:425-476).
+// Returns the latched event type, or 0xff when the reference queues nothing.
+__device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, const Bead &lo,
+                                                 const Bead &hi, int d, unsigned info,
+                                                 double &tout) {
+  const bool sw = lo.t < hi.t; // the reference swaps so that "i" has the later clock
+  const double ti = sw ? hi.t : lo.t, tj = sw ? lo.t : hi.t;
+  const double xi = sw ? hi.x : lo.x, yi = sw ? hi.y : lo.y, zi = sw ? hi.z : lo.z;
+  const double xj = sw ? lo.x : hi.x, yj = sw ? lo.y : hi.y, zj = sw ? lo.z : hi.z;
+  const double vxi = sw ? hi.vx : lo.vx, vyi = sw ? hi.vy : lo.vy, vzi = sw ? hi.vz : lo.vz;
+  const double vxj = sw ? lo.vx : hi.vx, vyj = sw ? lo.vy : hi.vy, vzj = sw ? lo.vz : hi.vz;
+  const double dt = ti - tj;
+  double dx = xj + vxj * dt - xi;
+  double dy = yj + vyj * dt - yi;
+  double dz = zj + vzj * dt - zi;
+  mindist3(a, dx, dy, dz);
+  const double dvx = vxj - vxi, dvy = vyj - vyi, dvz = vzj - vzi;
+  Quad q;
+  q.t = ti;
+  q.rv = dx * dvx + dy * dvy + dz * dvz;
+  q.vv = dvx * dvx + dvy * dvy + dvz * dvz;
+  q.rr = dx * dx + dy * dy + dz * dz;
+  q.rv2 = q.rv * q.rv;
+  if (d == 1) {
+    if (inner_time(q, a.near_min2, tout)) return HMC_EV_MIN_NEAREST;
+    tout = outer_time(q, a.near_max2);
+    return HMC_EV_MAX_NEAREST;
+  }
+  if (d == 2) {
+    if (inner_time(q, a.nnear_min2, tout)) return HMC_EV_MIN_NNEAREST;
+    tout = outer_time(q, a.nnear_max2);
+    return HMC_EV_MAX_NNEAREST;
+  }
+  const unsigned tb = info & 0x7fu;
+  const bool perm = (info & 0x80u) != 0;
+  const unsigned long long tmask = tb ? (1ull << (tb - 1)) : 0ull;
+  const bool bonded_t = (R.config & tmask) != 0;
+  const bool nonbonded_t = (~R.config & tmask) != 0;
+  // get_rc2_inner / get_rc2_outer, hardspheres.cc:394-419
+  const double r2i = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
+  double r2o = R.rc2;
+  if (perm && R.has_p_rc) r2o = R.p_rc2;
+  if (R.has_stair && nonbonded_t) r2o = R.stair2;
+  const unsigned nbonds = __popcll(R.config);
+  if (tmask && nbonds < R.max_nbonds && nonbonded_t && inner_time(q, r2i, tout))
+    return HMC_EV_MAX_NONLOCAL_INNER;
+  if (inner_time(q, a.rh2, tout)) return HMC_EV_MIN_NONLOCAL_INNER;
+  if (bonded_t || perm || (R.has_stair && nonbonded_t)) {
+    tout = outer_time(q, r2o);
+    return HMC_EV_MAX_NONLOCAL_OUTER;
+  }
+  return 0xffu;
+}
+
+// t_until_cell + if_cell, hardspheres.cc:560-693.  Returns false when the bead is
+// at rest (no event queued).
+__device__ __forceinline__ bool predict_cell(const KArgs &a, const Bead &b, int cx, int cy, int cz,
+                                             double &tout, unsigned &wall) {
+  double dx = a.lcell * double(cx) - b.x;
+  double dy = a.lcell * double(cy) - b.y;
+  double dz = a.lcell * double(cz) - b.z;
+  mindist3(a, dx, dy, dz);
+  bool cr = false;
+  double dt = 0.0;
+  if (b.vx > 0) {
+    dt = (dx + a.lcell) / b.vx;
+    cr = true;
+    wall = 0;
+  } else if (b.vx < 0) {
+    dt = dx / b.vx;
+    cr = true;
+    wall = 1;
+  }
+  if (b.vy > 0) {
+    const double c = (dy + a.lcell) / b.vy;
+    if (!cr || c < dt) {
+      cr = true;
+      dt = c;
+      wall = 2;
+    }
+  } else if (b.vy < 0) {
+    const double c = dy / b.vy;
+    if (!cr || c < dt) {
+      cr = true;
+      dt = c;
+      wall = 3;
+    }
+  }
+  if (b.vz > 0) {
+    const double c = (dz + a.lcell) / b.vz;
+    if (!cr || c < dt) {
+      cr = true;
+      dt = c;
+      wall = 4;
+    }
+  } else if (b.vz < 0) {
+    const double c = dz / b.vz;
+    if (!cr || c < dt) {
+      cr = true;
+      dt = c;
+      wall = 5;
+    }
+  }
+  tout = b.t + dt;
+  return cr;
+}
+
+// cells within the 27-neighbourhood (periodic), valid for ncell >= 4
+__device__ __forceinline__ bool adj1(int ca, int cb, int nc) {
+  int d = ca - cb;
+  if (d < 0) d += nc;
+  return d == 0 || d == 1 || d == nc - 1;
+}
+
+// -------------------------------------------------------------------- RNG --
+
+// Philox4x32-10 (Salmon et al., SC'11), counter-based: the stream of a replica
+// does not depend on scheduling.
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__device__ __forceinline__ double u53(unsigned hi, unsigned lo) {
+  const unsigned long long v = ((unsigned long long)hi << 32 | lo) >> 11;
+  return (double(v) + 0.5) * (1.0 / 9007199254740992.0); // (0,1)
+}
+
+// libstdc++ generate_canonical<double,53> on a 32-bit engine (bits/random.tcc:3349)
+__device__ __forceinline__ double canonical_words(unsigned w0, unsigned w1) {
+  double sum = double(w0) + double(w1) * 4294967296.0;
+  double r = sum / 18446744073709551616.0;
+  if (r >= 1.0) r = 0.99999999999999988898;
+  return r;
+}
+
+struct WordStream { // crankshaft word source: injected tape or Philox
+  const uint32_t *tape;
+  unsigned n, c;
+  bool underrun;
+  bool philox;
+  uint2 key;
+  unsigned c1, c2, c3; // counter words 1..3
+  uint4 buf;
+  unsigned buf_blk;
+};
+
+__device__ __forceinline__ unsigned ws_next(WordStream &w) {
+  if (w.philox) {
+    const unsigned blk = w.c >> 2;
+    if (blk != w.buf_blk) {
+      w.buf = philox4x32(make_uint4(blk, w.c1, w.c2, w.c3), w.key);
+      w.buf_blk = blk;
+    }
+    const unsigned q = w.c & 3u;
+    w.c++;
+    return q == 0 ? w.buf.x : q == 1 ? w.buf.y : q == 2 ? w.buf.z : w.buf.w;
+  }
+  if (w.c >= w.n) {
+    w.underrun = true;
+    w.c++;
+    return 0u;
+  }
+  return w.tape[w.c++];
+}
+
+// libstdc++ uniform_int_distribution on a 32-bit engine: Lemire's method
+// (bits/uniform_int_dist.h:255-281)
+__device__ __forceinline__ unsigned ws_uniform_int(WordStream &w, unsigned lo, unsigned hi) {
+  const unsigned range = hi - lo + 1u;
+  unsigned long long prod = (unsigned long long)ws_next(w) * range;
+  unsigned low = unsigned(prod);
+  if (low < range) {
+    const unsigned thr = (0u - range) % range;
+    while (low < thr && !w.underrun) {
+      prod = (unsigned long long)ws_next(w) * range;
+      low = unsigned(prod);
+    }
+  }
+  return unsigned(prod >> 32) + lo;
+}
+
+// ------------------------------------------------------------ trace / misc --
+
+__device__ __forceinline__ void trace_event(const KArgs &a, const Rep &R, int lane, unsigned type,
+                                            unsigned i, unsigned j, double t) {
+  if (R.tracing && lane == 0) {
+    const unsigned n = *a.trace_n;
+    if (n < a.trace_cap) {
+      hmc_event e;
+      e.t = t;
+      e.type = type;
+      e.i = i;
+      e.j = j;
+      e.pad = 0;
+      a.trace[n] = e;
+    }
+    *a.trace_n = n + 1;
+  }
+}
+
+// total_k_E + compute_hamiltonian, hardspheres.cc:1063-1082 (serial bead order)
+__device__ __forceinline__ double hamiltonian(const KArgs &a, const Rep &R, const Smem &s) {
+  double ke = 0.0;
+  const double hm = 0.5 * a.m;
+  for (int i = 0; i < a.nb; i++) {
+    const double vx2 = s.vx[i] * s.vx[i];
+    const double vy2 = s.vy[i] * s.vy[i];
+    const double vz2 = s.vz[i] * s.vz[i];
+    ke += hm * (vx2 + vy2 + vz2);
+  }
+  return ke + R.sb[R.config];
+}
+
+// --------------------------------------------------- step initialisation --
+
+// check_bond, hardspheres.cc:980-1004
+__device__ __forceinline__ bool check_bond_tol(double min2, double max2, double d2) {
+  const double tol = 1000000 * 2.220446049250313e-16;
+  return d2 > min2 * (1 - tol) && d2 < max2 * (1 + tol);
+}
+
+// min-image squared distance of beads i,j with the operand order pos[i]-pos[j]
+__device__ __forceinline__ double dist2_ij(const KArgs &a, const double *X, const double *Y,
+                                           const double *Z, int i, int j) {
+  double dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
+  mindist3(a, dx, dy, dz);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+// check_local_dist (hardspheres.cc:1006-1037, tolerance) / check_local_dist_if_crankshaft
+// (crankshaft.cc:88-123, strict) and check_nonlocal_dist (crankshaft.cc:125-171) over all
+// pairs, lane-parallel.  Returns bit0 = local ok, bit1 = nonlocal ok (group-uniform).
+template <int G>
+__device__ __forceinline__ unsigned check_constraints(const KArgs &a, const Rep &R, const double *X,
+                                                      const double *Y, const double *Z, bool strict,
+                                                      int lane, unsigned gmask) {
+  bool lok = true, nok = true;
+  for (int p = lane; p < a.npairs; p += G) {
+    const uchar2 ij = __ldg(&a.pair_ij[p]);
+    const int i = ij.x, j = ij.y, d = j - i;
+    if (d <= 2) {
+      // reference operand order here is pos[j]-pos[i]; dist2 is sign-symmetric
+      // only after squaring, so keep the order
+      double dx = X[j] - X[i], dy = Y[j] - Y[i], dz = Z[j] - Z[i];
+      mindist3(a, dx, dy, dz);
+      const double d2 = dx * dx + dy * dy + dz * dz;
+      const double mn = d == 1 ? a.near_min2 : a.nnear_min2;
+      const double mx = d == 1 ? a.near_max2 : a.nnear_max2;
+      const bool ok = strict ? (d2 > mn && d2 < mx) : check_bond_tol(mn, mx, d2);
+      lok = lok && ok;
+    } else {
+      const double d2 = dist2_ij(a, X, Y, Z, i, j);
+      const unsigned info = __ldg(&R.pinfo[p]);
+      bool ok = d2 > a.rh2;
+      if (info & 0x80u) {
+        const double r2i = R.has_p_rc ? R.p_rc2 : R.rc2;
+        ok = ok && (d2 < r2i);
+      }
+      if (R.has_stair && (info & 0x7fu)) ok = ok && (d2 < R.stair2);
+      nok = nok && ok;
+    }
+  }
+  const unsigned lb = __ballot_sync(gmask, !lok) & gmask;
+  const unsigned nbad = __ballot_sync(gmask, !nok) & gmask;
+  return (lb ? 0u : 1u) | (nbad ? 0u : 2u);
+}
+
+// initialize_system, main.cc:45-95: constraint checks, init_cells, velocities
+// (+ COM shift), and the full prediction fill of the event table.
+template <int G>
+__device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *normals,
+                          unsigned long long draw, int lane, unsigned gmask) {
+  const int nb = a.nb;
+  const unsigned ok = check_constraints<G>(a, R, s.x, s.y, s.z, false, lane, gmask);
+  if (!(ok & 1u)) R.err |= HMC_ERR_LOCAL_OVERLAP;
+  if (!(ok & 2u)) R.err |= HMC_ERR_NONLOCAL_OVERLAP;
+
+  // init_cells (hardspheres.cc:334-369) + raw velocity draws (init_vel :197-209)
+  for (int k = lane; k < nb; k += G) {
+    double x = s.x[k], y = s.y[k], z = s.z[k];
+    x -= floor(x * a.inv_l) * a.l; // Box::minpos
+    y -= floor(y * a.inv_l) * a.l;
+    z -= floor(z * a.inv_l) * a.l;
+    int ix = int(a.inv_lcell * x), iy = int(a.inv_lcell * y), iz = int(a.inv_lcell * z);
+    const int hi = a.ncell - 1;
+    ix = min(max(ix, 0), hi);
+    iy = min(max(iy, 0), hi);
+    iz = min(max(iz, 0), hi);
+    s.cx[k] = uint8_t(ix);
+    s.cy[k] = uint8_t(iy);
+    s.cz[k] = uint8_t(iz);
+    double nx, ny, nz;
+    if (a.rng_mode == HMC_RNG_INJECTED) {
+      nx = normals[3 * k + 0];
+      ny = normals[3 * k + 1];
+      nz = normals[3 * k + 2];
+    } else {
+      // Maxwell-Boltzmann by Box-Muller from two Philox blocks per bead;
+      // counter = (2k+c, draw_lo, draw_hi, replica)
+      const uint2 key = make_uint2(a.seed0, a.seed1);
+      const uint4 c0 = philox4x32(
+          make_uint4(2u * k, unsigned(draw), unsigned(draw >> 32), unsigned(R.r)), key);
+      const uint4 c1 = philox4x32(
+          make_uint4(2u * k + 1u, unsigned(draw), unsigned(draw >> 32), unsigned(R.r)), key);
+      const double r0 = sqrt(-2.0 * log(u53(c0.x, c0.y)));
+      double sn, cs;
+      sincospi(2.0 * u53(c0.z, c0.w), &sn, &cs);
+      const double r1 = sqrt(-2.0 * log(u53(c1.x, c1.y)));
+      double sn1, cs1;
+      sincospi(2.0 * u53(c1.z, c1.w), &sn1, &cs1);
+      nx = r0 * cs * a.vsigma;
+      ny = r0 * sn * a.vsigma;
+      nz = r1 * cs1 * a.vsigma;
+    }
+    s.vx[k] = nx;
+    s.vy[k] = ny;
+    s.vz[k] = nz;
+  }
+  __syncwarp(gmask);
+
+  // shift_vel_CM_to_0 (hardspheres.cc:173-194): serial sums in bead order
+  double tx = 0.0, ty = 0.0, tz = 0.0;
+  for (int i = 0; i < nb; i++) {
+    tx += s.vx[i];
+    ty += s.vy[i];
+    tz += s.vz[i];
+  }
+  const double cmx = tx / double(nb), cmy = ty / double(nb), cmz = tz / double(nb);
+  __syncwarp(gmask);
+  for (int k = lane; k < nb; k += G) {
+    s.vx[k] -= cmx;
+    s.vy[k] -= cmy;
+    s.vz[k] -= cmz;
+  }
+  __syncwarp(gmask);
+
+  // init_cell_events (hardspheres.cc:696-704)
+  for (int k = lane; k < nb; k += G) {
+    const Bead b = load_bead(s, k);
+    double t;
+    unsigned wall = 0;
+    const bool cr = predict_cell(a, b, s.cx[k], s.cy[k], s.cz[k], t, wall);
+    s.evt[k] = cr ? t : CUDART_INF;
+    s.evty[k] = uint8_t(wall);
+  }
+  // init_nearest/nnearest_bond_events (:885-937) and add_events_for_all_beads (:540-555)
+  for (int p = lane; p < a.npairs; p += G) {
+    const uchar2 ij = __ldg(&a.pair_ij[p]);
+    const int i = ij.x, j = ij.y, d = j - i;
+    double t = CUDART_INF;
+    unsigned ty = 0xffu;
+    bool doit = true;
+    if (d >= 3)
+      doit = adj1(s.cx[i], s.cx[j], a.ncell) && adj1(s.cy[i], s.cy[j], a.ncell) &&
+             adj1(s.cz[i], s.cz[j], a.ncell);
+    if (doit) {
+      const Bead lo = load_bead(s, i), hi = load_bead(s, j);
+      double tt;
+      ty = predict_pair(a, R, lo, hi, d, __ldg(&R.pinfo[p]), tt);
+      if (ty != 0xffu) t = tt;
+    }
+    s.evt[nb + p] = t;
+    s.evty[nb + p] = uint8_t(ty);
+  }
+  __syncwarp(gmask);
+}
+
+// --------------------------------------------------------- the event loop --
+
+// run_step, main.cc:97-149: process every event with t <= step_time, then advance
+// all beads to step_time.
+template <int G>
+__device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_time, int lane,
+                           unsigned gmask) {
+  const int nb = a.nb, nslots = a.nslots, nc = a.ncell;
+  unsigned guard = 0;
+  for (;;) {
+    // a step of the shipped configurations has 5e2-1e4 events; a runaway replica
+    // (non-finite state) is flagged and abandoned instead of hanging the device
+    if (++guard > a.max_events_per_step) {
+      R.err |= HMC_ERR_NAN;
+      break;
+    }
+    // ---- argmin over the event table (ties -> lowest slot) ----
+    double bt = CUDART_INF;
+    int bs = 0x7fffffff;
+    for (int q = lane; q < nslots; q += G) {
+      const double t = s.evt[q];
+      if (t < bt) {
+        bt = t;
+        bs = q;
+      }
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+      const double ot = __shfl_xor_sync(gmask, bt, off);
+      const int os = __shfl_xor_sync(gmask, bs, off);
+      if (ot < bt || (ot == bt && os < bs)) {
+        bt = ot;
+        bs = os;
+      }
+    }
+    if (!(bt <= step_time)) break;
+
+    const double t = bt;
+    int nbead; // beads whose slots are re-predicted
+    int bi, bj;
+    bool is_cell;
+    unsigned wall = 0;
+    if (bs < nb) {
+      // ---- BeadCellEvent, hardspheres.cc:1622-1645 ----
+      is_cell = true;
+      bi = bs;
+      bj = bs;
+      nbead = 1;
+      wall = s.evty[bs];
+      const Bead b = load_bead(s, bi);
+      int cx = s.cx[bi], cy = s.cy[bi], cz = s.cz[bi];
+      // new cell from the wall latched at prediction (t_until_cell :589-666)
+      if (wall == 0) cx = (cx + 1) % nc;
+      else if (wall == 1) cx = (cx - 1 + nc) % nc;
+      else if (wall == 2) cy = (cy + 1) % nc;
+      else if (wall == 3) cy = (cy - 1 + nc) % nc;
+      else if (wall == 4) cz = (cz + 1) % nc;
+      else cz = (cz - 1 + nc) % nc;
+      const double dt = t - b.t; // update_pos :1040-1047
+      const double nx = b.x + b.vx * dt, ny = b.y + b.vy * dt, nz = b.z + b.vz * dt;
+      __syncwarp(gmask);
+      if (lane == 0) {
+        s.x[bi] = nx;
+        s.y[bi] = ny;
+        s.z[bi] = nz;
+        s.tm[bi] = t;
+        s.cx[bi] = uint8_t(cx);
+        s.cy[bi] = uint8_t(cy);
+        s.cz[bi] = uint8_t(cz);
+      }
+      R.n_cell++;
+      trace_event(a, R, lane, HMC_EV_BEAD_CELL, bi, wall, t);
+    } else {
+      // ---- collision events, hardspheres.cc:1106-1620 ----
+      is_cell = false;
+      nbead = 2;
+      const int p = bs - nb;
+      const uchar2 ij = __ldg(&a.pair_ij[p]);
+      bi = ij.x;
+      bj = ij.y;
+      const unsigned ty = s.evty[bs];
+      Bead I = load_bead(s, bi), J = load_bead(s, bj);
+      // update_pos for both beads
+      const double dti = t - I.t, dtj = t - J.t;
+      I.x += I.vx * dti;
+      I.y += I.vy * dti;
+      I.z += I.vz * dti;
+      J.x += J.vx * dtj;
+      J.y += J.vy * dtj;
+      J.z += J.vz * dtj;
+      // final_vel (:1050-1061)
+      double dx = J.x - I.x, dy = J.y - I.y, dz = J.z - I.z;
+      mindist3(a, dx, dy, dz);
+      double sigma2;
+      bool has_dS = false;
+      double dS = 0.0;
+      unsigned long long tmask = 0ull;
+      if (ty == HMC_EV_MIN_NEAREST) sigma2 = a.near_min2;
+      else if (ty == HMC_EV_MAX_NEAREST) sigma2 = a.near_max2;
+      else if (ty == HMC_EV_MIN_NNEAREST) sigma2 = a.nnear_min2;
+      else if (ty == HMC_EV_MAX_NNEAREST) sigma2 = a.nnear_max2;
+      else if (ty == HMC_EV_MIN_NONLOCAL_INNER) sigma2 = a.rh2;
+      else {
+        const unsigned info = __ldg(&R.pinfo[p]);
+        const unsigned tb = info & 0x7fu;
+        const bool perm = (info & 0x80u) != 0;
+        tmask = tb ? (1ull << (tb - 1)) : 0ull;
+        if (ty == HMC_EV_MAX_NONLOCAL_INNER) {
+          // :1462-1466, s_of_inner_event :299-313
+          sigma2 = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
+          dS = R.sb[unsigned(R.config ^ tmask)] - R.sb[unsigned(R.config)];
+          has_dS = true;
+        } else {
+          // :1548-1558, s_of_outer_event :317-331
+          sigma2 = R.rc2;
+          if (perm && R.has_p_rc) sigma2 = R.p_rc2;
+          if (R.has_stair && (~R.config & tmask)) sigma2 = R.stair2;
+          if (tmask && (R.config & tmask)) {
+            dS = R.sb[unsigned(R.config ^ tmask)] - R.sb[unsigned(R.config)];
+            has_dS = true;
+          }
+        }
+      }
+      // v_after_coll (:258-295)
+      const double dvx = J.vx - I.vx, dvy = J.vy - I.vy, dvz = J.vz - I.vz;
+      const double mu = 0.5 * a.m;
+      double rv = (dx * dvx + dy * dvy + dz * dvz) / sigma2;
+      const double rv2 = rv * rv;
+      bool transmitted = false;
+      if (has_dS) {
+        const double dSn = 2 * dS / (sigma2 * mu);
+        if (rv2 > dSn) {
+          rv -= copysign(sqrt(rv2 - dSn), rv);
+          transmitted = true;
+        }
+      }
+      if (!transmitted) rv += rv;
+      const double px = rv * dx, py = rv * dy, pz = rv * dz;
+      I.vx += px / 2;
+      I.vy += py / 2;
+      I.vz += pz / 2;
+      J.vx -= px / 2;
+      J.vy -= py / 2;
+      J.vz -= pz / 2;
+      if (transmitted) {
+        R.config ^= tmask;
+        if (ty == HMC_EV_MAX_NONLOCAL_INNER) R.formed++;
+        else R.broken++;
+      }
+      __syncwarp(gmask);
+      if (lane == 0) {
+        s.x[bi] = I.x;
+        s.y[bi] = I.y;
+        s.z[bi] = I.z;
+        s.vx[bi] = I.vx;
+        s.vy[bi] = I.vy;
+        s.vz[bi] = I.vz;
+        s.tm[bi] = t;
+        s.x[bj] = J.x;
+        s.y[bj] = J.y;
+        s.z[bj] = J.z;
+        s.vx[bj] = J.vx;
+        s.vy[bj] = J.vy;
+        s.vz[bj] = J.vz;
+        s.tm[bj] = t;
+      }
+      R.n_coll++;
+      trace_event(a, R, lane, ty, bi, bj, t);
+    }
+    __syncwarp(gmask);
+
+    // ---- re-prediction ----
+    // collision: every slot touching bi or bj is rewritten (local wells always, nonlocal
+    // partners only inside the 27-cell neighbourhood, add_events_for_one_bead :507-536)
+    // crossing: only partners in the 9 newly adjacent cells, min-merged
+    // (add_events_for_bead_after_crossing :740-856); plus if_cell for each bead.
+    for (int qb = 0; qb < nbead; qb++) {
+      const int b = qb ? bj : bi;
+      const Bead B = load_bead(s, b);
+      const int bcx = s.cx[b], bcy = s.cy[b], bcz = s.cz[b];
+      {
+        double tc;
+        unsigned w = 0;
+        const bool cr = predict_cell(a, B, bcx, bcy, bcz, tc, w);
+        if (lane == 0) {
+          s.evt[b] = cr ? tc : CUDART_INF;
+          s.evty[b] = uint8_t(w);
+        }
+      }
+      // the cell coordinate that became adjacent through this crossing
+      const int axis = int(wall >> 1);
+      int far = (axis == 0 ? bcx : axis == 1 ? bcy : bcz) + ((wall & 1u) ? -1 : 1);
+      far = (far + nc) % nc;
+      for (int k = lane; k < nb; k += G) {
+        if (k == b) continue;
+        const int lo = min(b, k), hi = max(b, k), d = hi - lo;
+        const int slot = nb + pair_index(lo, hi, nb);
+        bool doit;
+        const int kcx = s.cx[k], kcy = s.cy[k], kcz = s.cz[k];
+        if (is_cell) {
+          if (d < 3) continue;
+          const int kax = axis == 0 ? kcx : axis == 1 ? kcy : kcz;
+          doit = kax == far && (axis == 0 || adj1(bcx, kcx, nc)) &&
+                 (axis == 1 || adj1(bcy, kcy, nc)) && (axis == 2 || adj1(bcz, kcz, nc));
+          if (!doit) continue;
+        } else {
+          doit = d < 3 || (adj1(bcx, kcx, nc) && adj1(bcy, kcy, nc) && adj1(bcz, kcz, nc));
+        }
+        double tnew = CUDART_INF;
+        unsigned ty = 0xffu;
+        if (doit) {
+          const Bead K = load_bead(s, k);
+          double tt;
+          ty = (b < k) ? predict_pair(a, R, B, K, d, __ldg(&R.pinfo[slot - nb]), tt)
+                       : predict_pair(a, R, K, B, d, __ldg(&R.pinfo[slot - nb]), tt);
+          if (ty != 0xffu) tnew = tt;
+        }
+        if (is_cell) {
+          if (tnew < s.evt[slot]) {
+            s.evt[slot] = tnew;
+            s.evty[slot] = uint8_t(ty);
+          }
+        } else {
+          s.evt[slot] = tnew;
+          s.evty[slot] = uint8_t(ty);
+        }
+      }
+      __syncwarp(gmask);
+    }
+  }
+  // advance every bead to step_time (main.cc:135-138)
+  for (int k = lane; k < nb; k += G) {
+    const double dt = step_time - s.tm[k];
+    s.x[k] += s.vx[k] * dt;
+    s.y[k] += s.vy[k] * dt;
+    s.z[k] += s.vz[k] * dt;
+    s.tm[k] = step_time;
+  }
+  __syncwarp(gmask);
+}
+
+// -------------------------------------------------------------- sampling --
+
+__device__ __forceinline__ void record_config_int(const KArgs &a, const Rep &R, int lane) {
+  if (a.cfg_cap && lane == 0) {
+    const unsigned n = a.cfg_n[R.r];
+    if (n < a.cfg_cap) a.cfg_int[size_t(R.r) * a.cfg_cap + n] = R.config;
+    a.cfg_n[R.r] = n + 1;
+  }
+}
+
+// body of run_trajectory after run_step, main.cc:199-225
+template <int G>
+__device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step, double e0,
+                            int lane, unsigned gmask) {
+  const int trans = R.r / a.replicas_per_trans;
+  // dist_between_nonlocal_beads (hardspheres.cc:1084-1104)
+  if (a.dist_cap || a.hist_bins) {
+    const unsigned nrow = a.dist_cap ? a.dist_n[R.r] : 0u;
+    for (int k = lane; k < int(R.tr->n_nonlocal); k += G) {
+      const int i = R.tr->nl_i[k], j = R.tr->nl_j[k];
+      const double d = sqrt(dist2_ij(a, s.x, s.y, s.z, i, j));
+      if (a.dist_cap && nrow < a.dist_cap)
+        a.dist[(size_t(R.r) * a.dist_cap + nrow) * a.dist_stride + k] = d;
+      if (a.hist_bins) {
+        int bin = int(d * a.hist_scale);
+        bin = min(max(bin, 0), int(a.hist_bins) - 1);
+        atomicAdd(&a.hist[(size_t(trans) * a.dist_stride + k) * a.hist_bins + bin], 1ull);
+      }
+    }
+    __syncwarp(gmask);
+    if (a.dist_cap && lane == 0) {
+      if (nrow >= a.dist_cap) R.err |= HMC_ERR_SAMPLE_OVERFLOW;
+      a.dist_n[R.r] = nrow + 1;
+    }
+  }
+  if (step % a.write_step == 0) {
+    if (lane == 0 && R.config < (unsigned long long)a.nstates)
+      atomicAdd(&a.acc[size_t(trans) * a.nstates + R.config], 1ull);
+    record_config_int(a, R, lane);
+    // unique_config: first recorded sample with config == 1 (main.cc:211-216)
+    if (R.config == 1ull && !a.uniq_found[R.r]) {
+      for (int k = lane; k < a.nb; k += G) {
+        double *up = a.uniq_pos + (size_t(R.r) * a.nb + k) * 3;
+        double *uv = a.uniq_vel + (size_t(R.r) * a.nb + k) * 3;
+        up[0] = s.x[k];
+        up[1] = s.y[k];
+        up[2] = s.z[k];
+        uv[0] = s.vx[k];
+        uv[1] = s.vy[k];
+        uv[2] = s.vz[k];
+      }
+      __syncwarp(gmask);
+      if (lane == 0) a.uniq_found[R.r] = 1;
+      __syncwarp(gmask);
+    }
+  }
+  const double e1 = hamiltonian(a, R, s);
+  const double ediff = fabs(1 - (e1 / e0));
+  if (!(ediff < 1e-6)) R.err |= HMC_ERR_ENERGY;
+}
+
+// ------------------------------------------------------------- crankshaft --
+
+// crankshaft (crankshaft.cc:224-262): Rodrigues rotation of the chain tail about the
+// bond (ind-1, ind), geometric checks, trial bitmask, Metropolis on s_bias.
+// Trial coordinates use the velocity arrays as scratch (velocities are redrawn at the
+// start of every MD step; they are saved to global memory before the first move).
+template <int G>
+__device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &ws,
+                            unsigned move_offset, unsigned n_moves, int lane, unsigned gmask) {
+  const int nb = a.nb;
+  double *tx = s.vx, *ty = s.vy, *tz = s.vz;
+  for (unsigned mv = 0; mv < n_moves; mv++) {
+    const unsigned start = ws.c;
+    unsigned attempts = 0;
+    bool ok = false;
+    do {
+      const unsigned ind = ws_uniform_int(ws, 1u, unsigned(nb - 2));
+      const unsigned cth = ws.c;
+      const unsigned w0 = ws_next(ws), w1 = ws_next(ws);
+      if (ws.underrun) break;
+      double sn, cs;
+      if (ws.philox) {
+        // uniform_real_distribution(0, 2*pi): canonical*(b-a)+a
+        const double th = canonical_words(w0, w1) * (2 * 3.14159265358979323846 - 0.0) + 0.0;
+        sincos(th, &sn, &cs);
+      } else {
+        sn = a.tape_sin[size_t(R.r) * a.tape_n + cth];
+        cs = a.tape_cos[size_t(R.r) * a.tape_n + cth];
+      }
+      attempts++;
+      // rodrigues_rotation, crankshaft.cc:11-73
+      double dx = s.x[ind] - s.x[ind - 1];
+      double dy = s.y[ind] - s.y[ind - 1];
+      double dz = s.z[ind] - s.z[ind - 1];
+      mindist3(a, dx, dy, dz);
+      const double inv = 1 / sqrt(dx * dx + dy * dy + dz * dz);
+      const double kx = dx * inv, ky = dy * inv, kz = dz * inv;
+      const double cth1 = 1 - cs;
+      const double Rxx = 1 + cth1 * (-kz * kz - ky * ky);
+      const double Rxy = -sn * kz + cth1 * ky * kx;
+      const double Rxz = sn * ky + cth1 * kz * kx;
+      const double Ryx = sn * kz + cth1 * kx * ky;
+      const double Ryy = 1 + cth1 * (-kz * kz - kx * kx);
+      const double Ryz = -sn * kx + cth1 * kz * ky;
+      const double Rzx = -sn * ky + cth1 * kx * kz;
+      const double Rzy = sn * kx + cth1 * ky * kz;
+      const double Rzz = 1 + cth1 * (-ky * ky - kx * kx);
+      const double px = s.x[ind], py = s.y[ind], pz = s.z[ind];
+      __syncwarp(gmask);
+      for (int k = lane; k < nb; k += G) {
+        if (k <= int(ind)) {
+          tx[k] = s.x[k];
+          ty[k] = s.y[k];
+          tz[k] = s.z[k];
+        } else {
+          double ox = s.x[k] - px, oy = s.y[k] - py, oz = s.z[k] - pz;
+          mindist3(a, ox, oy, oz);
+          double nx = Rxx * ox + Rxy * oy + Rxz * oz;
+          double ny = Ryx * ox + Ryy * oy + Ryz * oz;
+          double nz = Rzx * ox + Rzy * oy + Rzz * oz;
+          mindist3(a, nx, ny, nz);
+          tx[k] = px + nx;
+          ty[k] = py + ny;
+          tz[k] = pz + nz;
+        }
+      }
+      __syncwarp(gmask);
+      ok = check_constraints<G>(a, R, tx, ty, tz, true, lane, gmask) == 3u;
+    } while (!ok);
+    if (ws.underrun) {
+      ws.c = start;
+      R.err |= HMC_ERR_TAPE_UNDERRUN;
+      break;
+    }
+    // config_int, crankshaft.cc:175-205: only transient-bond pairs can set bits
+    unsigned long long trial = 0ull;
+    for (unsigned k = 0; k < R.tr->n_transient; k++) {
+      const int i = R.tr->tb_i[k], j = R.tr->tb_j[k];
+      const double d2 = dist2_ij(a, tx, ty, tz, i, j);
+      // first occurrence of a pair in the list owns it (std::find, config.h:34)
+      bool first = true;
+      for (unsigned q = 0; q < k; q++)
+        if (R.tr->tb_i[q] == i && R.tr->tb_j[q] == j) first = false;
+      if (first && !(d2 > R.rc2)) trial ^= (1ull << k);
+    }
+    // accept_move, crankshaft.cc:207-222
+    const double dS = R.sb[trial] - R.sb[R.config];
+    bool accept = true;
+    if (dS > 0) {
+      const unsigned w0 = ws_next(ws), w1 = ws_next(ws);
+      if (ws.underrun) {
+        ws.c = start;
+        R.err |= HMC_ERR_TAPE_UNDERRUN;
+        break;
+      }
+      const double u = canonical_words(w0, w1) * (1.0 - 0.0) + 0.0;
+      if (u > exp(-dS)) accept = false;
+    }
+    R.n_att += attempts;
+    if (accept) {
+      __syncwarp(gmask);
+      for (int k = lane; k < nb; k += G) {
+        s.x[k] = tx[k];
+        s.y[k] = ty[k];
+        s.z[k] = tz[k];
+      }
+      R.config = trial;
+      R.n_acc++;
+      __syncwarp(gmask);
+    }
+    // main.cc:232-236
+    const unsigned i = move_offset + mv;
+    for (unsigned j = 1; j < a.mc_write; j++)
+      if (i == (j * a.mc_moves) / a.mc_write) record_config_int(a, R, lane);
+  }
+}
+
+// -------------------------------------------------------------- the kernel --
+
+__device__ __forceinline__ double wl_gamma(const KArgs &a, unsigned iter_wl) {
+  return iter_wl == 0 ? a.gamma0 : 1.0 / double(iter_wl); // main.cc:283,302-303
+}
+
+template <int G> __global__ void __launch_bounds__(128) hmc_ensemble_kernel(const __grid_constant__ KArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & (G - 1);
+  const unsigned gmask = group_mask<G>();
+  const int group_in_cta = threadIdx.x / G;
+  const Smem s = carve(smem_raw + size_t(group_in_cta) * a.smem_per_replica, a.nb, a.nslots);
+  const int nb = a.nb;
+
+  for (;;) {
+    int r = 0;
+    if (lane == 0) r = int(atomicAdd(a.work_counter, 1u));
+    r = __shfl_sync(gmask, r, 0, G);
+    if (r >= a.n_replicas) break;
+
+    Rep R;
+    R.r = r;
+    const int trans = r / a.replicas_per_trans;
+    R.tr = a.trans + trans;
+    R.pinfo = a.pairinfo + size_t(trans) * a.npairs;
+    R.sb = a.s_bias + size_t(r) * a.nstates;
+    R.config = a.config[r];
+    R.rc2 = R.tr->rc2;
+    R.stair2 = R.tr->stair2;
+    R.p_rc2 = R.tr->p_rc2;
+    R.has_stair = R.tr->has_stair;
+    R.has_p_rc = R.tr->has_p_rc;
+    R.max_nbonds = R.tr->max_nbonds;
+    R.err = 0;
+    R.n_coll = R.n_cell = R.n_att = R.n_acc = R.formed = R.broken = 0;
+    R.tracing = (a.trace_cap != 0 && a.trace_replica == r);
+
+    // load the replica (bead clocks all equal t_now at a step boundary)
+    for (int k = lane; k < nb; k += G) {
+      const double *p = a.pos + (size_t(r) * nb + k) * 3;
+      s.x[k] = p[0];
+      s.y[k] = p[1];
+      s.z[k] = p[2];
+      const double *v = a.vel + (size_t(r) * nb + k) * 3;
+      s.vx[k] = v[0];
+      s.vy[k] = v[1];
+      s.vz[k] = v[2];
+      s.tm[k] = a.t_now;
+    }
+    __syncwarp(gmask);
+
+    WordStream ws;
+    ws.tape = a.tape_words ? a.tape_words + size_t(r) * a.tape_n : nullptr;
+    ws.n = a.tape_n;
+    ws.c = 0;
+    ws.underrun = false;
+    ws.philox = (a.rng_mode == HMC_RNG_PHILOX);
+    ws.key = make_uint2(a.seed0, a.seed1);
+    ws.c1 = ws.c2 = 0;
+    ws.c3 = unsigned(r);
+    ws.buf_blk = 0xffffffffu;
+
+    bool vel_dirty = false; // velocity arrays hold crankshaft scratch
+    auto save_vel = [&]() {
+      for (int k = lane; k < nb; k += G) {
+        double *v = a.vel + (size_t(r) * nb + k) * 3;
+        v[0] = s.vx[k];
+        v[1] = s.vy[k];
+        v[2] = s.vz[k];
+      }
+      __syncwarp(gmask);
+    };
+
+    if (a.op == HMC_OP_CRANK_ONLY) {
+      crank_moves<G>(a, R, s, ws, a.move_offset, a.count, lane, gmask);
+      vel_dirty = true;
+      if (lane == 0 && a.tape_consumed) a.tape_consumed[r] = ws.c;
+    } else {
+      unsigned long long draw = a.md_draw_base; // one draw index per initialize_system
+      unsigned inj = 0;                          // injected-normals row
+      auto normals_row = [&]() -> const double * {
+        return a.normals ? a.normals + (size_t(r) * a.count + inj) * size_t(nb) * 3 : nullptr;
+      };
+      for (unsigned it = 0; it < a.count; it++) {
+        if (a.phase == HMC_PHASE_WL) {
+          // wang_landau / run_trajectory_wl, main.cc:249-305
+          // RUN: `it` = outer iteration offset (nstates trajectories each);
+          // MD_ONLY: `it` = trajectory offset
+          const unsigned ntraj = (a.op == HMC_OP_RUN) ? unsigned(a.nstates) : 1u;
+          for (unsigned q = 0; q < ntraj; q++) {
+            const unsigned iter_wl =
+                (a.op == HMC_OP_RUN) ? a.first + it : (a.first + it) / unsigned(a.nstates);
+            init_step<G>(a, R, s, normals_row(), draw, lane, gmask);
+            draw++;
+            inj++;
+            const double e0 = hamiltonian(a, R, s);
+            for (unsigned st = iter_wl * a.nsteps_wl; st < (iter_wl + 1) * a.nsteps_wl; st++) {
+              run_events<G>(a, R, s, double(st) * a.del_t_wl, lane, gmask);
+              const double e1 = hamiltonian(a, R, s);
+              if (!(fabs(1 - (e1 / e0)) < 1e-6)) R.err |= HMC_ERR_ENERGY;
+            }
+            const double g = wl_gamma(a, iter_wl);
+            __syncwarp(gmask);
+            if (lane == 0) {
+              if (R.config == 0ull) R.sb[a.nstates - 1] -= g;
+              else R.sb[a.nstates - 1] += g;
+            }
+            __syncwarp(gmask);
+          }
+        } else {
+          const unsigned nsteps = (a.phase == HMC_PHASE_EQ) ? a.nsteps_eq : a.nsteps;
+          unsigned st0, st1;
+          if (a.op == HMC_OP_RUN) {
+            st0 = (a.first + it) * nsteps;
+            st1 = st0 + nsteps;
+          } else {
+            st0 = a.first + it;
+            st1 = st0 + 1;
+          }
+          for (unsigned st = st0; st < st1; st++) {
+            init_step<G>(a, R, s, normals_row(), draw, lane, gmask);
+            draw++;
+            inj++;
+            if (a.phase == HMC_PHASE_EQ) {
+              run_events<G>(a, R, s, double(st) * a.del_t, lane, gmask);
+            } else {
+              const double e0 = hamiltonian(a, R, s);
+              run_events<G>(a, R, s, double(st) * a.del_t, lane, gmask);
+              sample_step<G>(a, R, s, st, e0, lane, gmask);
+            }
+          }
+          if (a.op == HMC_OP_RUN && a.phase == HMC_PHASE_MAIN && a.mc_moves) {
+            save_vel();
+            const unsigned long long mcd = a.mc_draw_base + it;
+            ws.c = 0;
+            ws.c1 = unsigned(mcd);
+            ws.c2 = unsigned(mcd >> 32) | 0x80000000u;
+            ws.buf_blk = 0xffffffffu;
+            crank_moves<G>(a, R, s, ws, 0u, a.mc_moves, lane, gmask);
+            vel_dirty = true;
+          }
+        }
+      }
+    }
+
+    // store the replica back
+    __syncwarp(gmask);
+    for (int k = lane; k < nb; k += G) {
+      double *p = a.pos + (size_t(r) * nb + k) * 3;
+      p[0] = s.x[k];
+      p[1] = s.y[k];
+      p[2] = s.z[k];
+    }
+    if (!vel_dirty) save_vel();
+    if (lane == 0) {
+      a.config[r] = R.config;
+      if (R.err) atomicOr(&a.err[r], R.err);
+      const size_t base = size_t(a.n_trans) * a.nstates;
+      if (R.formed) atomicAdd(&a.acc[base + trans], R.formed);
+      if (R.broken) atomicAdd(&a.acc[base + a.n_trans + trans], R.broken);
+      unsigned long long *ev = a.acc + base + 2 * size_t(a.n_trans);
+      if (R.n_coll) atomicAdd(&ev[0], R.n_coll);
+      if (R.n_cell) atomicAdd(&ev[1], R.n_cell);
+      if (R.n_att) atomicAdd(&ev[2], R.n_att);
+      if (R.n_acc) atomicAdd(&ev[3], R.n_acc);
+    }
+    __syncwarp(gmask);
+  }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------- launcher --
+
+size_t hmc_smem_per_replica(int nb) {
+  const size_t npairs = size_t(nb) * (nb - 1) / 2;
+  const size_t nslots = nb + npairs;
+  size_t bytes = 8 * (7 * size_t(nb) + nslots) + nslots + 3 * size_t(nb);
+  return (bytes + 15) & ~size_t(15);
+}
+
+int hmc_pick_group(int nb) {
+  // lanes per replica: enough that one pass of the partner loop covers most beads
+  if (nb <= 10) return 8;
+  if (nb <= 24) return 16;
+  return 32;
+}
+
+template <int G>
+static cudaError_t launch_g(const KArgs &a, cudaStream_t stream, int *grid_out, int *block_out) {
+  const int block = 128;
+  const int groups_per_cta = block / G;
+  const size_t smem = size_t(groups_per_cta) * a.smem_per_replica;
+  cudaError_t e = cudaFuncSetAttribute(hmc_ensemble_kernel<G>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmc_ensemble_kernel<G>, block, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorInvalidConfiguration;
+  // persistent grid: a multiple of the SM count, never more CTAs than work
+  long long need = (a.n_replicas + groups_per_cta - 1) / groups_per_cta;
+  long long grid = (long long)sms * per_sm;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  hmc_ensemble_kernel<G><<<int(grid), block, smem, stream>>>(a);
+  if (grid_out) *grid_out = int(grid);
+  if (block_out) *block_out = block;
+  return cudaGetLastError();
+}
+
+cudaError_t hmc_launch(const KArgs &a, int group, cudaStream_t stream, int *grid_out,
+                       int *block_out) {
+  switch (group) {
+  case 8: return launch_g<8>(a, stream, grid_out, block_out);
+  case 16: return launch_g<16>(a, stream, grid_out, block_out);
+  default: return launch_g<32>(a, stream, grid_out, block_out);
+  }
+}

@@ -1,0 +1,310 @@
+"""ctypes mirror of the C-ABI (include/hybridmc_b200.h).
+
+`Engine` wraps one `hmc_handle`.  Method names follow the reference's functions
+(run_trajectory_eq / wang_landau / run_trajectory -> `run(PHASE_*)`,
+compute_entropy, g_test ...).  Nothing here computes trajectories: every call is
+forwarded to libhybridmc_b200.so, and a missing library or GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .params import HmcParams
+
+PHASE_EQ, PHASE_WL, PHASE_MAIN = 0, 1, 2
+
+ERR_LOCAL_OVERLAP, ERR_NONLOCAL_OVERLAP, ERR_ENERGY = 1, 2, 4
+ERR_NAN, ERR_TAPE_UNDERRUN, ERR_SAMPLE_OVERFLOW = 8, 16, 32
+
+EVENT_DTYPE = np.dtype([("t", "<f8"), ("type", "<u4"), ("i", "<u4"), ("j", "<u4"),
+                        ("pad", "<u4")])
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhybridmc_b200.so")
+
+# every symbol include/hybridmc_b200.h declares
+EXPORTS = [
+    "hmc_create", "hmc_destroy", "hmc_last_error", "hmc_abi_version",
+    "hmc_set_positions", "hmc_get_positions", "hmc_get_velocities", "hmc_set_config",
+    "hmc_get_config", "hmc_init_config_from_positions", "hmc_set_s_bias", "hmc_get_s_bias",
+    "hmc_reset_clocks", "hmc_reset_counts", "hmc_seed", "hmc_run", "hmc_sync",
+    "hmc_md_steps_injected", "hmc_crankshaft_injected", "hmc_get_counts",
+    "hmc_counts_device_ptr", "hmc_get_event_counts", "hmc_enable_samples", "hmc_get_dist",
+    "hmc_get_config_int", "hmc_enable_dist_hist", "hmc_get_dist_hist",
+    "hmc_get_unique_config", "hmc_enable_trace", "hmc_get_trace", "hmc_compute_entropy",
+    "hmc_compute_g_val", "hmc_g_test", "hmc_wl_outer_iterations", "hmc_get_launch_stats",
+]
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen the CUDA library; fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise EngineError(
+            "%s is missing: build it with `python -m hybridmc_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % path)
+    lib = C.CDLL(path)
+    lib.hmc_last_error.restype = C.c_char_p
+    lib.hmc_last_error.argtypes = [C.c_void_p]
+    lib.hmc_create.argtypes = [C.POINTER(HmcParams), C.c_int, C.c_int, C.c_int,
+                               C.POINTER(C.c_void_p)]
+    lib.hmc_compute_g_val.restype = C.c_double
+    lib.hmc_compute_g_val.argtypes = [C.c_void_p, C.c_int]
+    lib.hmc_wl_outer_iterations.restype = C.c_uint
+    lib.hmc_wl_outer_iterations.argtypes = [C.POINTER(HmcParams)]
+    lib.hmc_compute_entropy.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double]
+    lib.hmc_g_test.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
+                               C.c_void_p]
+    lib.hmc_enable_dist_hist.argtypes = [C.c_void_p, C.c_uint, C.c_double]
+    for name in ("hmc_destroy", "hmc_set_positions", "hmc_get_positions", "hmc_get_velocities",
+                 "hmc_set_config", "hmc_get_config", "hmc_init_config_from_positions",
+                 "hmc_reset_clocks", "hmc_reset_counts", "hmc_sync", "hmc_get_event_counts",
+                 "hmc_get_dist", "hmc_get_config_int", "hmc_get_dist_hist",
+                 "hmc_get_unique_config", "hmc_get_launch_stats", "hmc_counts_device_ptr"):
+        getattr(lib, name).argtypes = None
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One ensemble on one GPU: T transitions x R replicas each."""
+
+    def __init__(self, transitions, replicas_per_transition=1, device=0):
+        if isinstance(transitions, HmcParams):
+            transitions = [transitions]
+        self.lib = load_library()
+        self.T = len(transitions)
+        self.Rper = int(replicas_per_transition)
+        self.R = self.T * self.Rper
+        self.params = list(transitions)
+        self.p = self.params[0]
+        self.nb = self.p.nbeads
+        self.nstates = self.p.nstates
+        arr = (HmcParams * self.T)(*transitions)
+        h = C.c_void_p()
+        rc = self.lib.hmc_create(arr, self.T, self.Rper, int(device), C.byref(h))
+        if rc != 0:
+            raise EngineError(self.lib.hmc_last_error(None).decode())
+        self.h = h
+        self.n_nonlocal = max(p.n_nonlocal for p in transitions)
+        self._trace_cap = 0
+        self._dist_cap = 0
+        self._cfg_cap = 0
+        self._hist_bins = 0
+
+    # -- plumbing --
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(self.lib.hmc_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hmc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- state --
+    def set_positions(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(self.R, self.nb, 3)
+        self._ck(self.lib.hmc_set_positions(self.h, _p(pos)))
+
+    def get_positions(self):
+        out = np.empty((self.R, self.nb, 3))
+        self._ck(self.lib.hmc_get_positions(self.h, _p(out)))
+        return out
+
+    def get_velocities(self):
+        out = np.empty((self.R, self.nb, 3))
+        self._ck(self.lib.hmc_get_velocities(self.h, _p(out)))
+        return out
+
+    def set_config(self, cfg):
+        cfg = np.ascontiguousarray(np.broadcast_to(np.asarray(cfg, dtype=np.uint64), (self.R,)))
+        self._ck(self.lib.hmc_set_config(self.h, _p(cfg)))
+
+    def get_config(self):
+        out = np.empty(self.R, dtype=np.uint64)
+        self._ck(self.lib.hmc_get_config(self.h, _p(out)))
+        return out
+
+    def init_config_from_positions(self):
+        self._ck(self.lib.hmc_init_config_from_positions(self.h))
+
+    def set_s_bias(self, s_bias):
+        sb = np.ascontiguousarray(
+            np.broadcast_to(np.asarray(s_bias, dtype=np.float64), (self.T, self.nstates)))
+        self._ck(self.lib.hmc_set_s_bias(self.h, _p(sb), self.nstates))
+
+    def get_s_bias(self):
+        out = np.empty((self.R, self.nstates))
+        self._ck(self.lib.hmc_get_s_bias(self.h, _p(out), self.nstates))
+        return out
+
+    def init_s(self):
+        """init_s, src/entropy.cc:14-20."""
+        nb = self.p.n_transient
+        sb = np.array([3.0 * (nb - bin(i).count("1")) for i in range(self.nstates)])
+        self.set_s_bias(sb)
+        return sb
+
+    def reset_clocks(self):
+        self._ck(self.lib.hmc_reset_clocks(self.h))
+
+    def reset_counts(self):
+        self._ck(self.lib.hmc_reset_counts(self.h))
+
+    # -- production path --
+    def seed(self, s0, s1=0):
+        self._ck(self.lib.hmc_seed(self.h, C.c_uint32(s0), C.c_uint32(s1)))
+
+    def run(self, phase, first_iter, n_iters):
+        self._ck(self.lib.hmc_run(self.h, int(phase), C.c_uint(first_iter), C.c_uint(n_iters)))
+
+    def sync(self):
+        self._ck(self.lib.hmc_sync(self.h))
+
+    def wl_outer_iterations(self):
+        return int(self.lib.hmc_wl_outer_iterations(C.byref(self.p)))
+
+    # -- reference-exact path --
+    def md_steps_injected(self, phase, first_step, normals):
+        normals = np.ascontiguousarray(normals, dtype=np.float64)
+        nsteps = normals.size // (self.R * self.nb * 3)
+        assert normals.size == self.R * nsteps * self.nb * 3
+        self._ck(self.lib.hmc_md_steps_injected(self.h, int(phase), C.c_uint(first_step),
+                                                C.c_uint(nsteps), _p(normals)))
+
+    def crankshaft_injected(self, move_offset, n_moves, words, sin_tab, cos_tab):
+        words = np.ascontiguousarray(words, dtype=np.uint32).reshape(self.R, -1)
+        n = words.shape[1]
+        sin_tab = np.ascontiguousarray(sin_tab, dtype=np.float64).reshape(self.R, n)
+        cos_tab = np.ascontiguousarray(cos_tab, dtype=np.float64).reshape(self.R, n)
+        consumed = np.zeros(self.R, dtype=np.uint32)
+        self._ck(self.lib.hmc_crankshaft_injected(
+            self.h, C.c_uint(move_offset), C.c_uint(n_moves), _p(words), _p(sin_tab),
+            _p(cos_tab), C.c_uint(n), _p(consumed)))
+        return consumed
+
+    # -- results --
+    def get_counts(self):
+        cc = np.zeros((self.T, self.nstates), dtype=np.uint64)
+        formed = np.zeros(self.T, dtype=np.uint64)
+        broken = np.zeros(self.T, dtype=np.uint64)
+        err = np.zeros(self.R, dtype=np.uint32)
+        self._ck(self.lib.hmc_get_counts(self.h, _p(cc), self.nstates, _p(formed), _p(broken),
+                                         _p(err)))
+        return cc, formed, broken, err
+
+    def counts_device_ptr(self):
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.hmc_counts_device_ptr(self.h, C.byref(ptr), C.byref(n)))
+        return ptr.value, int(n.value)
+
+    def get_event_counts(self):
+        ev = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.hmc_get_event_counts(self.h, _p(ev)))
+        return ev
+
+    def enable_samples(self, dist_rows, config_int_cap=0):
+        self._ck(self.lib.hmc_enable_samples(self.h, C.c_uint(dist_rows), C.c_uint(config_int_cap)))
+        self._dist_cap, self._cfg_cap = dist_rows, config_int_cap
+
+    def get_dist(self):
+        stride = max(self.n_nonlocal, 1)
+        out = np.zeros((self.R, self._dist_cap, stride))
+        n = np.zeros(self.R, dtype=np.uint32)
+        self._ck(self.lib.hmc_get_dist(self.h, _p(out), _p(n)))
+        return out, n
+
+    def get_config_int(self):
+        out = np.zeros((self.R, self._cfg_cap), dtype=np.uint64)
+        n = np.zeros(self.R, dtype=np.uint32)
+        self._ck(self.lib.hmc_get_config_int(self.h, _p(out), _p(n)))
+        return out, n
+
+    def enable_dist_hist(self, nbins, rmax):
+        self._ck(self.lib.hmc_enable_dist_hist(self.h, C.c_uint(nbins), C.c_double(rmax)))
+        self._hist_bins = nbins
+
+    def get_dist_hist(self):
+        out = np.zeros((self.T, max(self.n_nonlocal, 1), self._hist_bins), dtype=np.uint64)
+        self._ck(self.lib.hmc_get_dist_hist(self.h, _p(out)))
+        return out
+
+    def get_unique_config(self):
+        pos = np.zeros((self.R, self.nb, 3))
+        vel = np.zeros((self.R, self.nb, 3))
+        found = np.zeros(self.R, dtype=np.uint8)
+        self._ck(self.lib.hmc_get_unique_config(self.h, _p(pos), _p(vel), _p(found)))
+        return pos, vel, found
+
+    def enable_trace(self, replica, capacity):
+        self._ck(self.lib.hmc_enable_trace(self.h, int(replica), C.c_uint(capacity)))
+        self._trace_cap = capacity
+
+    def get_trace(self):
+        buf = np.zeros(max(self._trace_cap, 1), dtype=EVENT_DTYPE)
+        n = C.c_uint()
+        self._ck(self.lib.hmc_get_trace(self.h, _p(buf), C.c_uint(self._trace_cap), C.byref(n)))
+        return buf[:min(n.value, self._trace_cap)], int(n.value)
+
+    def launch_stats(self):
+        n, ms = C.c_uint64(), C.c_float()
+        self._ck(self.lib.hmc_get_launch_stats(self.h, C.byref(n), C.byref(ms)))
+        return int(n.value), float(ms.value)
+
+
+# ---- entropy.cc mirror (host, O(nstates)) ---------------------------------------
+
+def compute_entropy(config_count, s_bias, pos_scale, neg_scale):
+    """compute_entropy, src/entropy.cc:36-69; returns the updated s_bias."""
+    lib = load_library()
+    cc = np.ascontiguousarray(config_count, dtype=np.uint64)
+    sb = np.array(s_bias, dtype=np.float64)
+    rc = lib.hmc_compute_entropy(_p(cc), _p(sb), len(cc), C.c_double(pos_scale),
+                                 C.c_double(neg_scale))
+    if rc != 0:
+        raise EngineError("hmc_compute_entropy failed")
+    return sb
+
+
+def compute_g_val(config_count):
+    lib = load_library()
+    cc = np.ascontiguousarray(config_count, dtype=np.uint64)
+    return float(lib.hmc_compute_g_val(_p(cc), len(cc)))
+
+
+def g_test(config_count, sig_level):
+    """g_test, src/entropy.cc:92-116 -> (accepted, g_val, g_crit, p_val)."""
+    lib = load_library()
+    cc = np.ascontiguousarray(config_count, dtype=np.uint64)
+    g, crit, pv = C.c_double(), C.c_double(), C.c_double()
+    ok = lib.hmc_g_test(_p(cc), len(cc), C.c_double(sig_level), C.byref(g), C.byref(crit),
+                        C.byref(pv))
+    return bool(ok), g.value, crit.value, pv.value

@@ -239,6 +239,10 @@ double hmc_compute_g_val(const uint64_t *config_count, int nstates);
 int hmc_g_test(const uint64_t *config_count, int nstates, double sig_level,
                double *g_val, double *g_crit, double *p_val);
 
+/* Number of outer Wang-Landau iterations the reference's gamma schedule performs
+ * (while gamma > gamma_f: ...; gamma = 1/iter_wl — main.cc:283-304). */
+unsigned hmc_wl_outer_iterations(const hmc_params *p);
+
 /* ---- launch statistics (for bench.py) ------------------------------------ */
 
 /* kernels launched by this handle so far, and the device time (ms, CUDA
