@@ -1,0 +1,132 @@
+"""Layer scheduler over the bond-state lattice — the batched counterpart of the
+reference's campaign driver (tools/init_json.py:14-130): the transitions of one
+lattice layer (same number of bonds already formed) are independent and run as ONE
+ensemble launch; layer L+1 starts from a structure harvested from layer L in which
+the new bond is formed (the reference passes it through `unique_config/pos` of the
+previous layer's HDF5 file, src/snapshot.cc:122-131).
+
+Also the per-transition estimator `run_transition_ensemble`: the phase loop of the
+reference's main (src/main.cc:411-491: equilibrate -> Wang-Landau -> G-test loop)
+driven over R replicas with pooled counts.
+"""
+import numpy as np
+
+from .engine import (PHASE_EQ, PHASE_MAIN, PHASE_WL, Engine, compute_entropy, g_test,
+                     init_pos_chain)
+from .params import params_from_json, transition_jsons
+
+
+def layers_of(master_json, seed_increment=1):
+    """[(layer, [(bits_in, bits_out, HmcParams)])] in BFS order."""
+    out = {}
+    for layer, bits_in, bits_out, d in transition_jsons(master_json, seed_increment):
+        out.setdefault(layer, []).append((bits_in, bits_out, params_from_json(d)))
+    return [(k, out[k]) for k in sorted(out)]
+
+
+def harvest_start_structures(master_json, device=0, replicas=128, eq_iters=4, max_rounds=400,
+                             seed=12345, verbose=False):
+    """Walk the lattice layer by layer with a small ensemble per transition and return
+    {bits: pos[nbeads][3]} — one valid structure per bond state (the empty state from
+    init_pos, every other one the first recorded configuration with the transient bond
+    formed, i.e. the reference's unique_config/pos row)."""
+    layers = layers_of(master_json)
+    nb_bonds = len(master_json["nonlocal_bonds"])
+    empty = tuple([False] * nb_bonds)
+    p0 = layers[0][1][0][2]
+    structures = {empty: init_pos_chain(p0)}
+    for layer, trans in layers:
+        params = [t[2] for t in trans]
+        with Engine(params, replicas, device) as e:
+            pos = np.stack([np.broadcast_to(structures[t[0]], (replicas,) + structures[t[0]].shape)
+                            for t in trans]).reshape(e.R, e.nb, 3)
+            e.set_positions(pos)
+            e.init_config_from_positions()
+            e.init_s()
+            e.seed(seed + layer, 77)
+            e.reset_clocks()
+            e.run(PHASE_EQ, 0, eq_iters)
+            e.init_config_from_positions()
+            e.reset_clocks()
+            missing = set(range(len(trans)))
+            it = 0
+            while missing and it < max_rounds:
+                e.run(PHASE_MAIN, it, 1)
+                it += 1
+                upos, _, found = e.get_unique_config()
+                found = found.reshape(len(trans), replicas)
+                for t in list(missing):
+                    w = np.nonzero(found[t])[0]
+                    if len(w):
+                        structures.setdefault(trans[t][1], upos.reshape(
+                            len(trans), replicas, e.nb, 3)[t, w[0]].copy())
+                        missing.discard(t)
+            _, _, _, err = e.get_counts()
+            if verbose:
+                print("layer", layer, "transitions", len(trans), "rounds", it, "missing",
+                      len(missing), "err", int(np.bitwise_or.reduce(err)))
+            if missing:
+                raise RuntimeError("no bonded configuration found for %d transitions of layer %d"
+                                   % (len(missing), layer))
+    return structures
+
+
+def run_transition_ensemble(params_list, start_pos, replicas, device=0, seed=(1, 2),
+                            iters_per_round=None, eq_iters=None, max_rounds=None, wl=True,
+                            hist_bins=0, hist_rmax=0.0, verbose=False):
+    """The reference's per-transition program (main.cc:411-491) for a batch of
+    transitions of one layer, R replicas each, pooled flat-histogram updates.
+
+    Per G-test round every replica runs `iters_per_round` iterations of run_trajectory
+    (default total_iter / R rounded up, so a round pools about as many recorded
+    configurations as one reference iteration ... times R when iters_per_round is
+    given explicitly).  Returns dict(s_bias[T][nstates], rounds, counts, events, err).
+    """
+    p = params_list[0]
+    T = len(params_list)
+    iters = iters_per_round or max(1, -(-p.total_iter // replicas))
+    eq = eq_iters if eq_iters is not None else max(1, min(p.total_iter_eq, 8))
+    cap = max_rounds or p.max_g_test_count
+    with Engine(params_list, replicas, device) as e:
+        pos = np.stack([np.broadcast_to(sp, (replicas,) + sp.shape) for sp in start_pos])
+        e.set_positions(pos.reshape(e.R, e.nb, 3))
+        e.seed(*seed)
+        e.init_config_from_positions()
+        s_bias = np.tile(e.init_s(), (T, 1))
+        if hist_bins:
+            e.enable_dist_hist(hist_bins, hist_rmax)
+        e.reset_clocks()
+        e.run(PHASE_EQ, 0, eq)
+        e.init_config_from_positions()
+        e.reset_clocks()
+        if wl:
+            e.run(PHASE_WL, 0, e.wl_outer_iterations())
+            # pooled Wang-Landau estimate: mean over the replicas of each transition
+            s_bias = e.get_s_bias().reshape(T, replicas, e.nstates).mean(axis=1)
+            e.set_s_bias(s_bias)
+        done = np.zeros(T, dtype=bool)
+        rounds = np.zeros(T, dtype=int)
+        counts = None
+        for rnd in range(cap):
+            e.reset_clocks()
+            e.reset_counts()
+            e.run(PHASE_MAIN, 0, iters)
+            counts, formed, broken, err = e.get_counts()
+            for t in range(T):
+                if done[t]:
+                    continue
+                s_bias[t] = compute_entropy(counts[t], s_bias[t], p.pos_scale, p.neg_scale)
+                rounds[t] += 1
+                ok, g, crit, pv = g_test(counts[t], p.sig_level)
+                if verbose:
+                    print("round", rnd, "transition", t, "s_bias", s_bias[t], "counts", counts[t],
+                          "ACCEPTED" if ok else "REJECTED", g, crit)
+                done[t] = ok
+            e.set_s_bias(s_bias)
+            if done.all():
+                break
+        out = dict(s_bias=s_bias, rounds=rounds, counts=counts, events=e.get_event_counts(),
+                   err=err, accepted=done)
+        if hist_bins:
+            out["dist_hist"] = e.get_dist_hist()
+        return out

@@ -171,7 +171,7 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.mc_draw_base = h->mc_draws;
   a.work_counter = h->d_work;
   a.smem_per_replica = uint32_t(hmc_smem_per_replica(h->nb));
-  a.max_events_per_step = 1u << 26;
+  a.max_events_per_step = 1u << 20; // ~100x the largest step of the shipped configs
 }
 
 int launch(hmc_handle h, const KArgs &a) {

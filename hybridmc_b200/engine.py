@@ -33,7 +33,7 @@ EXPORTS = [
     "hmc_counts_device_ptr", "hmc_get_event_counts", "hmc_enable_samples", "hmc_get_dist",
     "hmc_get_config_int", "hmc_enable_dist_hist", "hmc_get_dist_hist",
     "hmc_get_unique_config", "hmc_enable_trace", "hmc_get_trace", "hmc_compute_entropy",
-    "hmc_compute_g_val", "hmc_g_test", "hmc_wl_outer_iterations", "hmc_get_launch_stats",
+    "hmc_compute_g_val", "hmc_g_test", "hmc_wl_outer_iterations", "hmc_get_launch_stats", "hmc_init_pos_chain", "hmc_fp64_peak",
 ]
 
 _lib = None
@@ -308,3 +308,26 @@ def g_test(config_count, sig_level):
     ok = lib.hmc_g_test(_p(cc), len(cc), C.c_double(sig_level), C.byref(g), C.byref(crit),
                         C.byref(pv))
     return bool(ok), g.value, crit.value, pv.value
+
+
+def init_pos_chain(params, seeds=None):
+    """init_pos (src/hardspheres.cc:37-138) with std::mt19937(seed_seq(seeds))."""
+    lib = load_library()
+    if seeds is None:
+        seeds = list(params.seeds)[:params.n_seeds]
+    arr = (C.c_uint32 * len(seeds))(*[int(s) & 0xffffffff for s in seeds])
+    pos = np.zeros((params.nbeads, 3))
+    rc = lib.hmc_init_pos_chain(C.byref(params), arr, C.c_uint(len(seeds)), _p(pos))
+    if rc != 0:
+        raise EngineError("number of tries exceeded while placing bead in box")
+    return pos
+
+
+def fp64_peak(device=0):
+    """(DFMA TFLOP/s, DMUL+DADD TFLOP/s) measured on `device`."""
+    lib = load_library()
+    a, b = C.c_double(), C.c_double()
+    rc = lib.hmc_fp64_peak(int(device), C.byref(a), C.byref(b))
+    if rc != 0:
+        raise EngineError("hmc_fp64_peak failed (%d)" % rc)
+    return a.value, b.value

@@ -243,6 +243,18 @@ int hmc_g_test(const uint64_t *config_count, int nstates, double sig_level,
  * (while gamma > gamma_f: ...; gamma = 1/iter_wl — main.cc:283-304). */
 unsigned hmc_wl_outer_iterations(const hmc_params *p);
 
+/* init_pos (src/hardspheres.cc:37-138) for ONE chain on the host with
+ * std::mt19937(std::seed_seq(seeds)) — the reference's seeding contract
+ * (main.cc:379-380).  pos[nbeads][3].  Returns -1 where the reference throws
+ * "number of tries exceeded". */
+int hmc_init_pos_chain(const hmc_params *p, const uint32_t *seeds, unsigned n_seeds,
+                       double *pos);
+
+/* Measured FP64 issue rate of `device` in TFLOP/s: DFMA chains, and DMUL+DADD
+ * chains (the ceiling for this engine, which is compiled without FMA
+ * contraction for bit parity).  Roofline denominator for bench.py. */
+int hmc_fp64_peak(int device, double *fma_tflops, double *muladd_tflops);
+
 /* ---- launch statistics (for bench.py) ------------------------------------ */
 
 /* kernels launched by this handle so far, and the device time (ms, CUDA
