@@ -1,0 +1,130 @@
+"""CPU: the C-ABI library loads and exports every symbol include/hybridmc_b200.h declares
+(no compute calls), the host-side mirrors (params, campaign enumeration, entropy) behave
+like the reference's, and the product never falls back to the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import load_config
+from hybridmc_b200 import engine as eng
+from hybridmc_b200.params import HmcParams, params_from_json, transition_jsons
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from hybridmc_b200.build import build_library
+    build_library()
+    return eng.load_library()
+
+
+def test_header_symbols_exported():
+    lib = _lib()
+    hdr = open(os.path.join(ROOT, "include", "hybridmc_b200.h")).read()
+    declared = set(re.findall(r"\b(hmc_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"hmc_params", "hmc_event", "hmc_engine"}
+    assert declared == set(eng.EXPORTS), declared ^ set(eng.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.hmc_abi_version() == 1
+
+
+def test_params_struct_layout_matches_c():
+    # sizeof(hmc_params) as the C compiler sees it
+    import subprocess
+    import tempfile
+    src = '#include "hybridmc_b200.h"\n#include <stdio.h>\nint main(){printf("%zu", sizeof(hmc_params));}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o",
+                        os.path.join(d, "s")], check=True)
+        out = subprocess.run([os.path.join(d, "s")], capture_output=True, text=True).stdout
+    assert int(out) == C.sizeof(HmcParams)
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    _lib()
+    p = params_from_json(load_config("8bead_1bond"))
+    with pytest.raises(eng.EngineError) as ei:
+        eng.Engine(p, 1)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_create_validation_messages():
+    lib = _lib()
+    h = C.c_void_p()
+    p = params_from_json(load_config("8bead_1bond", ncell=3))
+    assert lib.hmc_create(C.byref(p), 1, 1, 0, C.byref(h)) != 0
+    assert b"ncell must be at least 4" in lib.hmc_last_error(None)  # main.cc:58-60
+    p = params_from_json(load_config("8bead_1bond", ncell=20))
+    assert lib.hmc_create(C.byref(p), 1, 1, 0, C.byref(h)) != 0
+    assert b"lcell must be at least rc" in lib.hmc_last_error(None)  # main.cc:62-69
+    with pytest.raises(RuntimeError):
+        params_from_json(load_config("8bead_1bond", stair=1.2))  # main.cc:535-537
+
+
+def test_params_from_json_mirrors_from_json():
+    d = load_config("crambin")
+    p = params_from_json(d)
+    assert (p.nbeads, p.ncell, p.n_nonlocal, p.n_transient, p.nstates) == (46, 9, 10, 10, 1024)
+    assert p.bond_list("nonlocal")[0] == (1, 33)
+    d2 = dict(d, nonlocal_bonds=[[33, 1]], transient_bonds=[[33, 1]])
+    assert params_from_json(d2).bond_list("transient") == [(1, 33)]  # normalised i<j
+    assert not p.has_stair and not p.has_p_rc
+
+
+def test_transition_enumeration_matches_init_json():
+    ts = transition_jsons(load_config("test"))
+    assert len(ts) == 12  # 3 bonds: 3 + 6 + 3 transitions
+    assert [t[0] for t in ts] == [0] * 3 + [1] * 6 + [2] * 3
+    assert ts[0][3]["seeds"] == [1, 1] and ts[0][3]["transient_bonds"] == [[2, 6]]
+    assert len(transition_jsons(load_config("crambin"))) == 5120
+    assert len(transition_jsons(load_config("50bead_9bond"))) == 2304
+
+
+def test_entropy_host_functions_match_oracle(oracle):
+    _lib()
+    rng = np.random.default_rng(0)
+    oracle.orc_compute_entropy.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double]
+    oracle.orc_compute_g_val.argtypes = [C.c_void_p, C.c_int]
+    oracle.orc_compute_g_val.restype = C.c_double
+    oracle.orc_g_test.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    for n in (2, 2, 4, 8, 1024):
+        cc = rng.integers(0, 500, size=n).astype(np.uint64)
+        if n == 2:
+            cc[rng.integers(0, 2)] = 0  # unvisited state branch
+        sb = rng.normal(size=n)
+        mine = eng.compute_entropy(cc, sb, 0.5, 0.1)
+        ref = sb.copy()
+        oracle.orc_compute_entropy(cc.ctypes.data, ref.ctypes.data, n, 0.5, 0.1)
+        assert np.array_equal(mine.view(np.uint64), ref.view(np.uint64))
+        assert eng.compute_g_val(cc) == oracle.orc_compute_g_val(cc.ctypes.data, n)
+        ok, g, crit, pv = eng.g_test(cc, 0.05)
+        g2, c2, p2 = C.c_double(), C.c_double(), C.c_double()
+        ok2 = oracle.orc_g_test(cc.ctypes.data, n, 0.05, C.addressof(g2), C.addressof(c2), C.addressof(p2))
+        assert (ok, g, crit, pv) == (bool(ok2), g2.value, c2.value, p2.value)
+
+
+def test_init_pos_chain_matches_oracle(oracle):
+    _lib()
+    from common import OracleRun
+    for name in ("8bead_1bond", "crambin"):
+        p = params_from_json(load_config(name))
+        pos = eng.init_pos_chain(p)
+        o = OracleRun(p, oracle)
+        assert np.array_equal(pos.view(np.uint64), o.init_pos().view(np.uint64))
+
+
+def test_product_does_not_reference_oracle():
+    """the shipped package / C sources never import, link or dlopen oracle/"""
+    for base, _, files in os.walk(os.path.join(ROOT, "hybridmc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                txt = open(os.path.join(base, f)).read()
+                assert "oracle_lib" not in txt and "libhmc_oracle" not in txt and "libhmc_ref" not in txt, f
