@@ -43,10 +43,11 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, out=None, defines=()):
+    """out/defines: build an experimental variant next to the default library."""
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), *nvcc_flags(), "-shared", "-o", LIB,
+    cmd = [nvcc_path(), *nvcc_flags(["-D" + d for d in defines]), "-shared", "-o", out or LIB,
            *[os.path.join(CSRC, s) for s in SOURCES],
            "-cudart", "static", "-Xlinker", "-l:libstdc++.so.6"]
     if verbose:
@@ -56,9 +57,12 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
     import sys
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                        out=outs[0] if outs else None, defines=defs))

@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -305,6 +306,10 @@ int hmc_create(const hmc_params *tr, int n_transitions, int replicas_per_transit
   h->npairs = h->nb * (h->nb - 1) / 2;
   h->nslots = h->nb + h->npairs;
   h->group = hmc_pick_group(h->nb);
+  if (const char *g = std::getenv("HMC_GROUP")) { // tuning knob: lanes per replica
+    const int v = std::atoi(g);
+    if (v == 8 || v == 16 || v == 32) h->group = v;
+  }
 
 #define CKC(call)                                                                        \
   do {                                                                                   \

@@ -4,8 +4,11 @@
 //
 // Design (B200-first, not a translation of the reference's heap + cell lists):
 //   * one GROUP of G lanes (G = 8, 16 or 32, a sub-warp) owns one replica for the
-//     whole launch; groups pull replicas from a global work counter, so there is no
-//     per-step barrier between replicas (event counts per step vary by 10-70 %).
+//     whole launch; the 32/G groups of a warp run in LOCKSTEP (every branch that
+//     contains a shuffle or sync is warp-uniform, finished groups are predicated off),
+//     because partial-mask __syncwarp/__shfl_sync compile to a slow MATCH/REDUX/BRA.DIV
+//     sequence on sm_100a.  Warps pull batches of replicas from a global work counter,
+//     so there is no barrier between warps (event counts per step vary by 10-70 %).
 //   * the replica lives in shared memory as SoA bead arrays (x,y,z,vx,vy,vz,clock),
 //     per-bead 3-D cell indices and an EVENT TABLE with one slot per bead (its next
 //     cell crossing) and one slot per bead pair (its next predicted collision, with
@@ -33,6 +36,11 @@
 #include "hmc_internal.h"
 
 #include <math_constants.h>
+
+// register budget: 128 threads x HMC_MIN_BLOCKS CTAs per SM
+#ifndef HMC_MIN_BLOCKS
+#define HMC_MIN_BLOCKS 4
+#endif
 
 namespace {
 
@@ -74,6 +82,7 @@ struct Rep {
   unsigned err;
   unsigned long long n_coll, n_cell, n_att, n_acc, formed, broken;
   bool tracing;
+  bool live; // false: a clone filling an idle group of the warp; no global side effects
 };
 
 template <int G> __device__ __forceinline__ unsigned group_mask() {
@@ -89,29 +98,32 @@ __device__ __forceinline__ int pair_index(int i, int j, int nb) {
   return i * (2 * nb - i - 1) / 2 + (j - i - 1);
 }
 
+// std::round (half away from zero), exact for every finite x: x - trunc(x) is exact,
+// so the comparison with 0.5 sees the true fraction.  5 instructions instead of the
+// libdevice sequence.
+__device__ __forceinline__ double round_away(double x) {
+  const double r = trunc(x);
+  const double f = x - r;
+  return (fabs(f) >= 0.5) ? r + copysign(1.0, x) : r;
+}
+
+// d - round(d/l)*l (Box::mindist, box.h:22-26).  For |d/l| < 1.5 — always, unless the
+// unwrapped chain is longer than 1.5 boxes — round() is 0 or +-1, so the product is
+// +-0 or +-l exactly and one compare + select + copysign replaces trunc/round/multiply;
+// the general form stays as a rarely taken branch.  Bit-identical either way.
+__device__ __forceinline__ double mindist1(const KArgs &a, double d) {
+  const double t = d * a.inv_l;
+  const double at = fabs(t);
+  double corr = copysign(at >= 0.5 ? a.l : 0.0, t);
+  if (at >= 1.5) corr = round_away(t) * a.l;
+  return d - corr;
+}
+
 // Box::mindist, box.h:22-26
 __device__ __forceinline__ void mindist3(const KArgs &a, double &dx, double &dy, double &dz) {
-  dx -= round(dx * a.inv_l) * a.l;
-  dy -= round(dy * a.inv_l) * a.l;
-  dz -= round(dz * a.inv_l) * a.l;
-}
-
-struct Quad {
-  double t, rv, vv, rr, rv2;
-};
-
-// t_until_inner_coll, hardspheres.cc:217-240
-__device__ __forceinline__ bool inner_time(const Quad &q, double s2, double &tout) {
-  if (!(q.rv < 0)) return false;
-  const double rad1 = q.vv * (q.rr - s2);
-  if (!(q.rv2 > rad1)) return false;
-  tout = q.t + (-q.rv - sqrt(q.rv2 - rad1)) / q.vv;
-  return true;
-}
-// t_until_outer_coll, hardspheres.cc:244-254
-__device__ __forceinline__ double outer_time(const Quad &q, double s2) {
-  const double rad1 = q.vv * (q.rr - s2);
-  return q.t + (-q.rv + sqrt(q.rv2 - rad1)) / q.vv;
+  dx = mindist1(a, dx);
+  dy = mindist1(a, dy);
+  dz = mindist1(a, dz);
 }
 
 struct Bead {
@@ -130,40 +142,46 @@ __device__ __forceinline__ Bead load_bead(const Smem &s, int k) {
   return b;
 }
 
-// delta_tpv (hardspheres.cc:372-392) for the ordered pair lo<hi, followed by the
-// type logic of if_nearest_bond / if_nnearest_bond (:863-923) or if_coll (:425-476).
-// Returns the latched event type, or 0xff when the reference queues nothing.
-__device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, const Bead &lo,
-                                                 const Bead &hi, int d, unsigned info,
-                                                 double &tout) {
-  const bool sw = lo.t < hi.t; // the reference swaps so that "i" has the later clock
-  const double ti = sw ? hi.t : lo.t, tj = sw ? lo.t : hi.t;
-  const double xi = sw ? hi.x : lo.x, yi = sw ? hi.y : lo.y, zi = sw ? hi.z : lo.z;
-  const double xj = sw ? lo.x : hi.x, yj = sw ? lo.y : hi.y, zj = sw ? lo.z : hi.z;
-  const double vxi = sw ? hi.vx : lo.vx, vyi = sw ? hi.vy : lo.vy, vzi = sw ? hi.vz : lo.vz;
-  const double vxj = sw ? lo.vx : hi.vx, vyj = sw ? lo.vy : hi.vy, vzj = sw ? lo.vz : hi.vz;
+// delta_tpv (hardspheres.cc:372-392) followed by the type logic of if_nearest_bond /
+// if_nnearest_bond (:863-923) or if_coll (:425-476).  Returns the latched event type,
+// or 0xff when the reference queues nothing.
+//
+// Every pair needs exactly ONE root of |dr + dv tau|^2 = sigma^2.  Which one (inner
+// root at the lower radius, or outer root at the upper radius) is decided with the
+// reference's comparisons only (rv < 0, rv^2 > vv (rr - sigma^2)); then one sqrt and
+// one division are evaluated with the operand values the reference's chosen branch
+// uses, so the result is bit-identical.  The body is written with selects only, so
+// that all lanes of a warp (and both replica groups in it) stay converged through
+// the sqrt / division sequences.
+//
+// Beads are passed as indices (p, q) with p_is_lo telling which one is lower: the
+// reference starts from (i,j) = (lo,hi) and swaps iff times[lo] < times[hi], so "i" is
+// the bead with the later clock and, on a tie, the lower index.
+__device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, const Smem &s,
+                                                 int p, int q, bool p_is_lo, int d,
+                                                 unsigned info, bool want, double &tout) {
+  // choose the roles by INDEX and load each bead once (no 64-bit selects)
+  const double tp = s.tm[p], tq = s.tm[q];
+  const bool sw = p_is_lo ? (tp < tq) : !(tq < tp); // true: "i" is q
+  const int bi_ = sw ? q : p, bj_ = sw ? p : q;
+  const double ti = sw ? tq : tp, tj = sw ? tp : tq;
+  const double xi = s.x[bi_], yi = s.y[bi_], zi = s.z[bi_];
+  const double xj = s.x[bj_], yj = s.y[bj_], zj = s.z[bj_];
+  const double vxi = s.vx[bi_], vyi = s.vy[bi_], vzi = s.vz[bi_];
+  const double vxj = s.vx[bj_], vyj = s.vy[bj_], vzj = s.vz[bj_];
   const double dt = ti - tj;
   double dx = xj + vxj * dt - xi;
   double dy = yj + vyj * dt - yi;
   double dz = zj + vzj * dt - zi;
   mindist3(a, dx, dy, dz);
   const double dvx = vxj - vxi, dvy = vyj - vyi, dvz = vzj - vzi;
-  Quad q;
-  q.t = ti;
-  q.rv = dx * dvx + dy * dvy + dz * dvz;
-  q.vv = dvx * dvx + dvy * dvy + dvz * dvz;
-  q.rr = dx * dx + dy * dy + dz * dz;
-  q.rv2 = q.rv * q.rv;
-  if (d == 1) {
-    if (inner_time(q, a.near_min2, tout)) return HMC_EV_MIN_NEAREST;
-    tout = outer_time(q, a.near_max2);
-    return HMC_EV_MAX_NEAREST;
-  }
-  if (d == 2) {
-    if (inner_time(q, a.nnear_min2, tout)) return HMC_EV_MIN_NNEAREST;
-    tout = outer_time(q, a.nnear_max2);
-    return HMC_EV_MAX_NNEAREST;
-  }
+  const double rv = dx * dvx + dy * dvy + dz * dvz;
+  const double vv = dvx * dvx + dvy * dvy + dvz * dvz;
+  const double rr = dx * dx + dy * dy + dz * dz;
+  const double rv2 = rv * rv;
+  const bool approaching = rv < 0;
+  const bool local = d <= 2, near = d == 1;
+  // nonlocal bond bookkeeping (info == 0 for local pairs)
   const unsigned tb = info & 0x7fu;
   const bool perm = (info & 0x80u) != 0;
   const unsigned long long tmask = tb ? (1ull << (tb - 1)) : 0ull;
@@ -171,18 +189,31 @@ __device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, c
   const bool nonbonded_t = (~R.config & tmask) != 0;
   // get_rc2_inner / get_rc2_outer, hardspheres.cc:394-419
   const double r2i = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
-  double r2o = R.rc2;
-  if (perm && R.has_p_rc) r2o = R.p_rc2;
-  if (R.has_stair && nonbonded_t) r2o = R.stair2;
-  const unsigned nbonds = __popcll(R.config);
-  if (tmask && nbonds < R.max_nbonds && nonbonded_t && inner_time(q, r2i, tout))
-    return HMC_EV_MAX_NONLOCAL_INNER;
-  if (inner_time(q, a.rh2, tout)) return HMC_EV_MIN_NONLOCAL_INNER;
-  if (bonded_t || perm || (R.has_stair && nonbonded_t)) {
-    tout = outer_time(q, r2o);
-    return HMC_EV_MAX_NONLOCAL_OUTER;
-  }
-  return 0xffu;
+  double r2o = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
+  r2o = (R.has_stair && nonbonded_t) ? R.stair2 : r2o;
+  const bool capcand = tmask && (unsigned(__popcll(R.config)) < R.max_nbonds) && nonbonded_t;
+  // first inner candidate: well minimum (local) / bond radius (capture) / hard core
+  const double s_in1 = local ? (near ? a.near_min2 : a.nnear_min2) : (capcand ? r2i : a.rh2);
+  const bool hit1 = approaching && (rv2 > vv * (rr - s_in1)); // t_until_inner_coll :217-240
+  // a failed capture falls through to the hard core (if_coll :457-467)
+  const bool hit2 = !local && capcand && !hit1 && approaching && (rv2 > vv * (rr - a.rh2));
+  const bool inner = hit1 || hit2;
+  const double s_out = local ? (near ? a.near_max2 : a.nnear_max2) : r2o;
+  const double s2 = hit1 ? s_in1 : (hit2 ? a.rh2 : s_out);
+  const bool outer_ok = local || bonded_t || perm || (R.has_stair && nonbonded_t);
+  unsigned ty;
+  if (local) ty = (near ? HMC_EV_MIN_NEAREST : HMC_EV_MIN_NNEAREST) + (inner ? 0u : 1u);
+  else ty = hit1 ? (capcand ? HMC_EV_MAX_NONLOCAL_INNER : HMC_EV_MIN_NONLOCAL_INNER)
+                 : (hit2 ? HMC_EV_MIN_NONLOCAL_INNER : HMC_EV_MAX_NONLOCAL_OUTER);
+  // Lanes whose result is not needed (pair not predicted by the reference, or no event)
+  // get harmless operands: a negative radicand or a NaN/zero dividend would send the
+  // whole warp through the slow-path subroutines of sqrt / division.
+  const bool valid = want && (inner || outer_ok);
+  const double rad1 = vv * (rr - s2);
+  const double root = sqrt(valid ? rv2 - rad1 : 1.0);
+  const double num = inner ? (-rv - root) : (-rv + root); // :237 / :253
+  tout = ti + (valid ? num : 1.0) / (valid ? vv : 1.0);
+  return valid ? ty : 0xffu;
 }
 
 // t_until_cell + if_cell, hardspheres.cc:560-693.  Returns false when the bead is
@@ -324,7 +355,7 @@ __device__ __forceinline__ unsigned ws_uniform_int(WordStream &w, unsigned lo, u
 
 __device__ __forceinline__ void trace_event(const KArgs &a, const Rep &R, int lane, unsigned type,
                                             unsigned i, unsigned j, double t) {
-  if (R.tracing && lane == 0) {
+  if (R.tracing && R.live && lane == 0) {
     const unsigned n = *a.trace_n;
     if (n < a.trace_cap) {
       hmc_event e;
@@ -401,8 +432,8 @@ __device__ __forceinline__ unsigned check_constraints(const KArgs &a, const Rep 
       nok = nok && ok;
     }
   }
-  const unsigned lb = __ballot_sync(gmask, !lok) & gmask;
-  const unsigned nbad = __ballot_sync(gmask, !nok) & gmask;
+  const unsigned lb = __ballot_sync(0xffffffffu, !lok) & gmask;
+  const unsigned nbad = __ballot_sync(0xffffffffu, !nok) & gmask;
   return (lb ? 0u : 1u) | (nbad ? 0u : 2u);
 }
 
@@ -457,7 +488,7 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
     s.vy[k] = ny;
     s.vz[k] = nz;
   }
-  __syncwarp(gmask);
+  __syncwarp();
 
   // shift_vel_CM_to_0 (hardspheres.cc:173-194): serial sums in bead order
   double tx = 0.0, ty = 0.0, tz = 0.0;
@@ -467,13 +498,13 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
     tz += s.vz[i];
   }
   const double cmx = tx / double(nb), cmy = ty / double(nb), cmz = tz / double(nb);
-  __syncwarp(gmask);
+  __syncwarp();
   for (int k = lane; k < nb; k += G) {
     s.vx[k] -= cmx;
     s.vy[k] -= cmy;
     s.vz[k] -= cmz;
   }
-  __syncwarp(gmask);
+  __syncwarp();
 
   // init_cell_events (hardspheres.cc:696-704)
   for (int k = lane; k < nb; k += G) {
@@ -495,245 +526,264 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
       doit = adj1(s.cx[i], s.cx[j], a.ncell) && adj1(s.cy[i], s.cy[j], a.ncell) &&
              adj1(s.cz[i], s.cz[j], a.ncell);
     if (doit) {
-      const Bead lo = load_bead(s, i), hi = load_bead(s, j);
       double tt;
-      ty = predict_pair(a, R, lo, hi, d, __ldg(&R.pinfo[p]), tt);
+      ty = predict_pair(a, R, s, i, j, true, d, __ldg(&R.pinfo[p]), true, tt);
       if (ty != 0xffu) t = tt;
     }
     s.evt[nb + p] = t;
     s.evty[nb + p] = uint8_t(ty);
   }
-  __syncwarp(gmask);
+  __syncwarp();
 }
 
 // --------------------------------------------------------- the event loop --
 
 // run_step, main.cc:97-149: process every event with t <= step_time, then advance
 // all beads to step_time.
+//
+// The body is one instruction path for collisions and cell crossings alike (selects
+// instead of branches): the replica groups that share a warp execute it in lockstep,
+// and a crossing simply discards the collision arithmetic it did not need.
 template <int G>
 __device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_time, int lane,
                            unsigned gmask) {
   const int nb = a.nb, nslots = a.nslots, nc = a.ncell;
   unsigned guard = 0;
+  bool overrun = false;
   for (;;) {
     // a step of the shipped configurations has 5e2-1e4 events; a runaway replica
     // (non-finite state) is flagged and abandoned instead of hanging the device
     if (++guard > a.max_events_per_step) {
       R.err |= HMC_ERR_NAN;
-      break;
+      overrun = true;
     }
     // ---- argmin over the event table (ties -> lowest slot) ----
     double bt = CUDART_INF;
     int bs = 0x7fffffff;
     for (int q = lane; q < nslots; q += G) {
       const double t = s.evt[q];
-      if (t < bt) {
-        bt = t;
-        bs = q;
-      }
+      const bool lt = t < bt;
+      bt = lt ? t : bt;
+      bs = lt ? q : bs;
     }
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) {
-      const double ot = __shfl_xor_sync(gmask, bt, off);
-      const int os = __shfl_xor_sync(gmask, bs, off);
-      if (ot < bt || (ot == bt && os < bs)) {
-        bt = ot;
-        bs = os;
-      }
+      const double ot = __shfl_xor_sync(0xffffffffu, bt, off);
+      const int os = __shfl_xor_sync(0xffffffffu, bs, off);
+      const bool take = ot < bt || (ot == bt && os < bs);
+      bt = take ? ot : bt;
+      bs = take ? os : bs;
     }
-    if (!(bt <= step_time)) break;
+    // groups whose step is finished idle (predicated off) until every group of the
+    // warp is done
+    const bool has = (bt <= step_time) && !overrun;
+    if (!__any_sync(0xffffffffu, has)) break;
+    bs = has ? bs : 0;
 
     const double t = bt;
-    int nbead; // beads whose slots are re-predicted
-    int bi, bj;
-    bool is_cell;
-    unsigned wall = 0;
-    if (bs < nb) {
-      // ---- BeadCellEvent, hardspheres.cc:1622-1645 ----
-      is_cell = true;
-      bi = bs;
-      bj = bs;
-      nbead = 1;
-      wall = s.evty[bs];
-      const Bead b = load_bead(s, bi);
-      int cx = s.cx[bi], cy = s.cy[bi], cz = s.cz[bi];
-      // new cell from the wall latched at prediction (t_until_cell :589-666)
-      if (wall == 0) cx = (cx + 1) % nc;
-      else if (wall == 1) cx = (cx - 1 + nc) % nc;
-      else if (wall == 2) cy = (cy + 1) % nc;
-      else if (wall == 3) cy = (cy - 1 + nc) % nc;
-      else if (wall == 4) cz = (cz + 1) % nc;
-      else cz = (cz - 1 + nc) % nc;
-      const double dt = t - b.t; // update_pos :1040-1047
-      const double nx = b.x + b.vx * dt, ny = b.y + b.vy * dt, nz = b.z + b.vz * dt;
-      __syncwarp(gmask);
-      if (lane == 0) {
-        s.x[bi] = nx;
-        s.y[bi] = ny;
-        s.z[bi] = nz;
-        s.tm[bi] = t;
-        s.cx[bi] = uint8_t(cx);
-        s.cy[bi] = uint8_t(cy);
-        s.cz[bi] = uint8_t(cz);
+    const bool is_cell = bs < nb;
+    const int nbead = is_cell ? 1 : 2; // beads whose slots are re-predicted
+    const int pidx = is_cell ? 0 : bs - nb;
+    const uchar2 ij = __ldg(&a.pair_ij[pidx]);
+    const int bi = is_cell ? bs : int(ij.x);
+    const int bj = is_cell ? bs : int(ij.y);
+    const unsigned ty = s.evty[bs]; // latched type, or the wall of a crossing
+    const unsigned wall = is_cell ? ty : 0u;
+
+    Bead I = load_bead(s, bi), J = load_bead(s, bj);
+    int cxn = s.cx[bi], cyn = s.cy[bi], czn = s.cz[bi];
+    // BeadCellEvent (hardspheres.cc:1622-1645): new cell from the wall latched at
+    // prediction (t_until_cell :589-666)
+    if (is_cell) {
+      cxn = wall == 0 ? (cxn + 1) % nc : wall == 1 ? (cxn - 1 + nc) % nc : cxn;
+      cyn = wall == 2 ? (cyn + 1) % nc : wall == 3 ? (cyn - 1 + nc) % nc : cyn;
+      czn = wall == 4 ? (czn + 1) % nc : wall == 5 ? (czn - 1 + nc) % nc : czn;
+    }
+    // update_pos (:1040-1047) for both beads (the same bead twice for a crossing)
+    const double dti = t - I.t, dtj = t - J.t;
+    I.x += I.vx * dti;
+    I.y += I.vy * dti;
+    I.z += I.vz * dti;
+    J.x += J.vx * dtj;
+    J.y += J.vy * dtj;
+    J.z += J.vz * dtj;
+    // collision events, hardspheres.cc:1106-1620: final_vel (:1050-1061)
+    double dx = J.x - I.x, dy = J.y - I.y, dz = J.z - I.z;
+    mindist3(a, dx, dy, dz);
+    const unsigned info = is_cell ? 0u : unsigned(__ldg(&R.pinfo[pidx]));
+    const unsigned tb = info & 0x7fu;
+    const bool perm = (info & 0x80u) != 0;
+    const unsigned long long tmask = tb ? (1ull << (tb - 1)) : 0ull;
+    const double r2p = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
+    // radius of the wall that was hit
+    double sigma2 = a.rh2;
+    sigma2 = ty == HMC_EV_MIN_NEAREST ? a.near_min2 : sigma2;
+    sigma2 = ty == HMC_EV_MAX_NEAREST ? a.near_max2 : sigma2;
+    sigma2 = ty == HMC_EV_MIN_NNEAREST ? a.nnear_min2 : sigma2;
+    sigma2 = ty == HMC_EV_MAX_NNEAREST ? a.nnear_max2 : sigma2;
+    sigma2 = ty == HMC_EV_MAX_NONLOCAL_INNER ? r2p : sigma2; // :1462-1466
+    if (ty == HMC_EV_MAX_NONLOCAL_OUTER)                     // :1548-1552
+      sigma2 = (R.has_stair && (~R.config & tmask)) ? R.stair2 : r2p;
+    sigma2 = (is_cell || !has) ? 1.0 : sigma2;
+    // entropy step of bond events: s_of_inner_event :299-313 / s_of_outer_event :317-331
+    const bool capture = !is_cell && ty == HMC_EV_MAX_NONLOCAL_INNER;
+    const bool escape = !is_cell && ty == HMC_EV_MAX_NONLOCAL_OUTER && tmask && (R.config & tmask);
+    const bool has_dS = capture || escape;
+    double dS = 0.0;
+    if (has_dS) dS = R.sb[unsigned(R.config ^ tmask)] - R.sb[unsigned(R.config)];
+    // v_after_coll (:258-295)
+    const double dvx = J.vx - I.vx, dvy = J.vy - I.vy, dvz = J.vz - I.vz;
+    const double mu = 0.5 * a.m;
+    // (a crossing or an idle group divides 1 by 1: a zero dividend takes the slow path)
+    const bool coll = has && !is_cell;
+    double rv = (coll ? dx * dvx + dy * dvy + dz * dvz : 1.0) / sigma2;
+    const double rv2 = rv * rv;
+    bool transmitted = false;
+    if (has_dS) {
+      const double dSn = 2 * dS / (sigma2 * mu);
+      if (rv2 > dSn) {
+        rv -= copysign(sqrt(rv2 - dSn), rv);
+        transmitted = true;
       }
-      R.n_cell++;
-      trace_event(a, R, lane, HMC_EV_BEAD_CELL, bi, wall, t);
-    } else {
-      // ---- collision events, hardspheres.cc:1106-1620 ----
-      is_cell = false;
-      nbead = 2;
-      const int p = bs - nb;
-      const uchar2 ij = __ldg(&a.pair_ij[p]);
-      bi = ij.x;
-      bj = ij.y;
-      const unsigned ty = s.evty[bs];
-      Bead I = load_bead(s, bi), J = load_bead(s, bj);
-      // update_pos for both beads
-      const double dti = t - I.t, dtj = t - J.t;
-      I.x += I.vx * dti;
-      I.y += I.vy * dti;
-      I.z += I.vz * dti;
-      J.x += J.vx * dtj;
-      J.y += J.vy * dtj;
-      J.z += J.vz * dtj;
-      // final_vel (:1050-1061)
-      double dx = J.x - I.x, dy = J.y - I.y, dz = J.z - I.z;
-      mindist3(a, dx, dy, dz);
-      double sigma2;
-      bool has_dS = false;
-      double dS = 0.0;
-      unsigned long long tmask = 0ull;
-      if (ty == HMC_EV_MIN_NEAREST) sigma2 = a.near_min2;
-      else if (ty == HMC_EV_MAX_NEAREST) sigma2 = a.near_max2;
-      else if (ty == HMC_EV_MIN_NNEAREST) sigma2 = a.nnear_min2;
-      else if (ty == HMC_EV_MAX_NNEAREST) sigma2 = a.nnear_max2;
-      else if (ty == HMC_EV_MIN_NONLOCAL_INNER) sigma2 = a.rh2;
-      else {
-        const unsigned info = __ldg(&R.pinfo[p]);
-        const unsigned tb = info & 0x7fu;
-        const bool perm = (info & 0x80u) != 0;
-        tmask = tb ? (1ull << (tb - 1)) : 0ull;
-        if (ty == HMC_EV_MAX_NONLOCAL_INNER) {
-          // :1462-1466, s_of_inner_event :299-313
-          sigma2 = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
-          dS = R.sb[unsigned(R.config ^ tmask)] - R.sb[unsigned(R.config)];
-          has_dS = true;
-        } else {
-          // :1548-1558, s_of_outer_event :317-331
-          sigma2 = R.rc2;
-          if (perm && R.has_p_rc) sigma2 = R.p_rc2;
-          if (R.has_stair && (~R.config & tmask)) sigma2 = R.stair2;
-          if (tmask && (R.config & tmask)) {
-            dS = R.sb[unsigned(R.config ^ tmask)] - R.sb[unsigned(R.config)];
-            has_dS = true;
-          }
-        }
-      }
-      // v_after_coll (:258-295)
-      const double dvx = J.vx - I.vx, dvy = J.vy - I.vy, dvz = J.vz - I.vz;
-      const double mu = 0.5 * a.m;
-      double rv = (dx * dvx + dy * dvy + dz * dvz) / sigma2;
-      const double rv2 = rv * rv;
-      bool transmitted = false;
-      if (has_dS) {
-        const double dSn = 2 * dS / (sigma2 * mu);
-        if (rv2 > dSn) {
-          rv -= copysign(sqrt(rv2 - dSn), rv);
-          transmitted = true;
-        }
-      }
-      if (!transmitted) rv += rv;
-      const double px = rv * dx, py = rv * dy, pz = rv * dz;
+    }
+    rv = transmitted ? rv : rv + rv;
+    const double px = rv * dx, py = rv * dy, pz = rv * dz;
+    if (!is_cell) {
       I.vx += px / 2;
       I.vy += py / 2;
       I.vz += pz / 2;
       J.vx -= px / 2;
       J.vy -= py / 2;
       J.vz -= pz / 2;
-      if (transmitted) {
-        R.config ^= tmask;
-        if (ty == HMC_EV_MAX_NONLOCAL_INNER) R.formed++;
-        else R.broken++;
-      }
-      __syncwarp(gmask);
-      if (lane == 0) {
-        s.x[bi] = I.x;
-        s.y[bi] = I.y;
-        s.z[bi] = I.z;
-        s.vx[bi] = I.vx;
-        s.vy[bi] = I.vy;
-        s.vz[bi] = I.vz;
-        s.tm[bi] = t;
-        s.x[bj] = J.x;
-        s.y[bj] = J.y;
-        s.z[bj] = J.z;
-        s.vx[bj] = J.vx;
-        s.vy[bj] = J.vy;
-        s.vz[bj] = J.vz;
-        s.tm[bj] = t;
-      }
-      R.n_coll++;
-      trace_event(a, R, lane, ty, bi, bj, t);
     }
-    __syncwarp(gmask);
+    if (transmitted && has) {
+      R.config ^= tmask;
+      if (capture) R.formed++;
+      else R.broken++;
+    }
+    R.n_cell += (has && is_cell) ? 1u : 0u;
+    R.n_coll += (has && !is_cell) ? 1u : 0u;
+    __syncwarp();
+    if (!has) {
+      // nothing to write
+    } else if (lane == 0) {
+      s.x[bi] = I.x;
+      s.y[bi] = I.y;
+      s.z[bi] = I.z;
+      s.vx[bi] = I.vx;
+      s.vy[bi] = I.vy;
+      s.vz[bi] = I.vz;
+      s.tm[bi] = t;
+      s.cx[bi] = uint8_t(cxn);
+      s.cy[bi] = uint8_t(cyn);
+      s.cz[bi] = uint8_t(czn);
+    } else if (lane == 1 && !is_cell) {
+      s.x[bj] = J.x;
+      s.y[bj] = J.y;
+      s.z[bj] = J.z;
+      s.vx[bj] = J.vx;
+      s.vy[bj] = J.vy;
+      s.vz[bj] = J.vz;
+      s.tm[bj] = t;
+    }
+    if (has) trace_event(a, R, lane, is_cell ? unsigned(HMC_EV_BEAD_CELL) : ty, bi, is_cell ? wall : bj, t);
+    __syncwarp();
 
     // ---- re-prediction ----
     // collision: every slot touching bi or bj is rewritten (local wells always, nonlocal
     // partners only inside the 27-cell neighbourhood, add_events_for_one_bead :507-536)
     // crossing: only partners in the 9 newly adjacent cells, min-merged
     // (add_events_for_bead_after_crossing :740-856); plus if_cell for each bead.
-    for (int qb = 0; qb < nbead; qb++) {
+
+    // if_cell (:678-693) for the 1 or 2 beads: one lane per (bead, axis) evaluates its
+    // wall time (one division each, in parallel), then the reference's x,y,z order with
+    // strict '<' is applied to the three candidates.
+    {
+      const int qb = lane >= 3 ? 1 : 0, ax = lane - 3 * qb; // lanes 0-2: bead bi, 3-5: bead bj
+      const bool on = lane < 6;
       const int b = qb ? bj : bi;
-      const Bead B = load_bead(s, b);
-      const int bcx = s.cx[b], bcy = s.cy[b], bcz = s.cz[b];
-      {
-        double tc;
-        unsigned w = 0;
-        const bool cr = predict_cell(a, B, bcx, bcy, bcz, tc, w);
-        if (lane == 0) {
-          s.evt[b] = cr ? tc : CUDART_INF;
-          s.evty[b] = uint8_t(w);
+      const double *P = ax == 0 ? s.x : ax == 1 ? s.y : s.z;
+      const double *V = ax == 0 ? s.vx : ax == 1 ? s.vy : s.vz;
+      const uint8_t *Cc = ax == 0 ? s.cx : ax == 1 ? s.cy : s.cz;
+      const double v = on ? V[b] : 1.0;
+      const double pp = on ? P[b] : 0.0;
+      const double cc = on ? double(Cc[b]) : 0.0;
+      const double dd = mindist1(a, a.lcell * cc - pp);
+      const double numer = v > 0 ? dd + a.lcell : dd;
+      const double cand = numer / v;
+      const int code = (on && v != 0.0 ? 1 : 0) | (v < 0 ? 2 : 0); // bit0 valid, bit1 negative wall
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const double c0 = __shfl_sync(0xffffffffu, cand, 3 * q + 0, G);
+        const double c1 = __shfl_sync(0xffffffffu, cand, 3 * q + 1, G);
+        const double c2 = __shfl_sync(0xffffffffu, cand, 3 * q + 2, G);
+        const int v0 = __shfl_sync(0xffffffffu, code, 3 * q + 0, G);
+        const int v1 = __shfl_sync(0xffffffffu, code, 3 * q + 1, G);
+        const int v2 = __shfl_sync(0xffffffffu, code, 3 * q + 2, G);
+        bool cr = (v0 & 1) != 0;
+        double dtc = cr ? c0 : 0.0;
+        unsigned w = unsigned(v0 >> 1);
+        const bool t1 = (v1 & 1) && (!cr || c1 < dtc);
+        dtc = t1 ? c1 : dtc;
+        w = t1 ? 2u + unsigned(v1 >> 1) : w;
+        cr = cr || t1;
+        const bool t2 = (v2 & 1) && (!cr || c2 < dtc);
+        dtc = t2 ? c2 : dtc;
+        w = t2 ? 4u + unsigned(v2 >> 1) : w;
+        cr = cr || t2;
+        if (has && lane == 0 && q < nbead) {
+          const int bq = q ? bj : bi;
+          s.evt[bq] = cr ? s.tm[bq] + dtc : CUDART_INF;
+          s.evty[bq] = uint8_t(w);
         }
       }
-      // the cell coordinate that became adjacent through this crossing
+    }
+
+    // partner predictions, both beads in one flattened lane loop
+    {
       const int axis = int(wall >> 1);
-      int far = (axis == 0 ? bcx : axis == 1 ? bcy : bcz) + ((wall & 1u) ? -1 : 1);
-      far = (far + nc) % nc;
-      for (int k = lane; k < nb; k += G) {
-        if (k == b) continue;
+      const int bcx0 = s.cx[bi], bcy0 = s.cy[bi], bcz0 = s.cz[bi];
+      const int bcx1 = s.cx[bj], bcy1 = s.cy[bj], bcz1 = s.cz[bj];
+      // the cell coordinate that became adjacent through a crossing
+      int far = (axis == 0 ? bcx0 : axis == 1 ? bcy0 : bcz0) + ((wall & 1u) ? -1 : 1);
+      far = far < 0 ? far + nc : (far >= nc ? far - nc : far);
+      const int nitem = nbead * nb;
+      // warp-uniform trip count: 2*nb unless every group of the warp has a crossing
+      const int nloop = __any_sync(0xffffffffu, has && !is_cell) ? 2 * nb : nb;
+      for (int base = 0; base < nloop; base += G) {
+        const int idx = base + lane;
+        const bool second = idx >= nb;
+        const int b = second ? bj : bi;
+        int k = second ? idx - nb : idx;
+        const bool in_range = idx < nitem;
+        k = in_range ? k : b;
         const int lo = min(b, k), hi = max(b, k), d = hi - lo;
-        const int slot = nb + pair_index(lo, hi, nb);
-        bool doit;
+        const int slot = nb + (k == b ? 0 : pair_index(lo, hi, nb));
+        const int bcx = second ? bcx1 : bcx0, bcy = second ? bcy1 : bcy0,
+                  bcz = second ? bcz1 : bcz0;
         const int kcx = s.cx[k], kcy = s.cy[k], kcz = s.cz[k];
-        if (is_cell) {
-          if (d < 3) continue;
-          const int kax = axis == 0 ? kcx : axis == 1 ? kcy : kcz;
-          doit = kax == far && (axis == 0 || adj1(bcx, kcx, nc)) &&
-                 (axis == 1 || adj1(bcy, kcy, nc)) && (axis == 2 || adj1(bcz, kcz, nc));
-          if (!doit) continue;
-        } else {
-          doit = d < 3 || (adj1(bcx, kcx, nc) && adj1(bcy, kcy, nc) && adj1(bcz, kcz, nc));
-        }
-        double tnew = CUDART_INF;
-        unsigned ty = 0xffu;
-        if (doit) {
-          const Bead K = load_bead(s, k);
-          double tt;
-          ty = (b < k) ? predict_pair(a, R, B, K, d, __ldg(&R.pinfo[slot - nb]), tt)
-                       : predict_pair(a, R, K, B, d, __ldg(&R.pinfo[slot - nb]), tt);
-          if (ty != 0xffu) tnew = tt;
-        }
-        if (is_cell) {
-          if (tnew < s.evt[slot]) {
-            s.evt[slot] = tnew;
-            s.evty[slot] = uint8_t(ty);
-          }
-        } else {
+        const bool ax_ok = adj1(bcx, kcx, nc), ay_ok = adj1(bcy, kcy, nc),
+                   az_ok = adj1(bcz, kcz, nc);
+        const int kax = axis == 0 ? kcx : axis == 1 ? kcy : kcz;
+        // which (b,k) the reference predicts at this event
+        const bool want_cell = d >= 3 && kax == far && (axis == 0 || ax_ok) &&
+                               (axis == 1 || ay_ok) && (axis == 2 || az_ok);
+        const bool want_coll = d < 3 || (ax_ok && ay_ok && az_ok);
+        const bool active = has && in_range && k != b;
+        const bool doit = active && (is_cell ? want_cell : want_coll);
+        double tt;
+        const unsigned pty =
+            predict_pair(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), doit, tt);
+        const bool have = doit && pty != 0xffu;
+        const double tnew = have ? tt : CUDART_INF;
+        // collision: overwrite (or clear) the slot; crossing: keep the earlier of old/new
+        const bool store = active && (is_cell ? (have && tnew < s.evt[slot]) : true);
+        if (store) {
           s.evt[slot] = tnew;
-          s.evty[slot] = uint8_t(ty);
+          s.evty[slot] = uint8_t(pty);
         }
       }
-      __syncwarp(gmask);
+      __syncwarp();
     }
   }
   // advance every bead to step_time (main.cc:135-138)
@@ -744,13 +794,13 @@ __device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_ti
     s.z[k] += s.vz[k] * dt;
     s.tm[k] = step_time;
   }
-  __syncwarp(gmask);
+  __syncwarp();
 }
 
 // -------------------------------------------------------------- sampling --
 
 __device__ __forceinline__ void record_config_int(const KArgs &a, const Rep &R, int lane) {
-  if (a.cfg_cap && lane == 0) {
+  if (a.cfg_cap && lane == 0 && R.live) {
     const unsigned n = a.cfg_n[R.r];
     if (n < a.cfg_cap) a.cfg_int[size_t(R.r) * a.cfg_cap + n] = R.config;
     a.cfg_n[R.r] = n + 1;
@@ -768,26 +818,28 @@ __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step
     for (int k = lane; k < int(R.tr->n_nonlocal); k += G) {
       const int i = R.tr->nl_i[k], j = R.tr->nl_j[k];
       const double d = sqrt(dist2_ij(a, s.x, s.y, s.z, i, j));
-      if (a.dist_cap && nrow < a.dist_cap)
+      if (a.dist_cap && nrow < a.dist_cap && R.live)
         a.dist[(size_t(R.r) * a.dist_cap + nrow) * a.dist_stride + k] = d;
-      if (a.hist_bins) {
+      if (a.hist_bins && R.live) {
         int bin = int(d * a.hist_scale);
         bin = min(max(bin, 0), int(a.hist_bins) - 1);
         atomicAdd(&a.hist[(size_t(trans) * a.dist_stride + k) * a.hist_bins + bin], 1ull);
       }
     }
-    __syncwarp(gmask);
-    if (a.dist_cap && lane == 0) {
+    __syncwarp();
+    if (a.dist_cap && lane == 0 && R.live) {
       if (nrow >= a.dist_cap) R.err |= HMC_ERR_SAMPLE_OVERFLOW;
       a.dist_n[R.r] = nrow + 1;
     }
   }
   if (step % a.write_step == 0) {
-    if (lane == 0 && R.config < (unsigned long long)a.nstates)
+    if (lane == 0 && R.live && R.config < (unsigned long long)a.nstates)
       atomicAdd(&a.acc[size_t(trans) * a.nstates + R.config], 1ull);
     record_config_int(a, R, lane);
     // unique_config: first recorded sample with config == 1 (main.cc:211-216)
-    if (R.config == 1ull && !a.uniq_found[R.r]) {
+    const bool take = R.live && R.config == 1ull && !a.uniq_found[R.r];
+    __syncwarp();
+    if (take) {
       for (int k = lane; k < a.nb; k += G) {
         double *up = a.uniq_pos + (size_t(R.r) * a.nb + k) * 3;
         double *uv = a.uniq_vel + (size_t(R.r) * a.nb + k) * 3;
@@ -798,10 +850,9 @@ __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step
         uv[1] = s.vy[k];
         uv[2] = s.vz[k];
       }
-      __syncwarp(gmask);
       if (lane == 0) a.uniq_found[R.r] = 1;
-      __syncwarp(gmask);
     }
+    __syncwarp();
   }
   const double e1 = hamiltonian(a, R, s);
   const double ediff = fabs(1 - (e1 / e0));
@@ -819,25 +870,39 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
                             unsigned move_offset, unsigned n_moves, int lane, unsigned gmask) {
   const int nb = a.nb;
   double *tx = s.vx, *ty = s.vy, *tz = s.vz;
+  bool dead = false; // tape ran out: this group sits out the remaining moves
   for (unsigned mv = 0; mv < n_moves; mv++) {
     const unsigned start = ws.c;
     unsigned attempts = 0;
     bool ok = false;
-    do {
-      const unsigned ind = ws_uniform_int(ws, 1u, unsigned(nb - 2));
-      const unsigned cth = ws.c;
-      const unsigned w0 = ws_next(ws), w1 = ws_next(ws);
-      if (ws.underrun) break;
-      double sn, cs;
-      if (ws.philox) {
-        // uniform_real_distribution(0, 2*pi): canonical*(b-a)+a
-        const double th = canonical_words(w0, w1) * (2 * 3.14159265358979323846 - 0.0) + 0.0;
-        sincos(th, &sn, &cs);
-      } else {
-        sn = a.tape_sin[size_t(R.r) * a.tape_n + cth];
-        cs = a.tape_cos[size_t(R.r) * a.tape_n + cth];
+    // retry loop of crankshaft.cc:245-253; warp-uniform: groups that already hold a
+    // valid trial are predicated off until every group of the warp has one
+    for (;;) {
+      const bool need = !ok && !dead;
+      if (!__any_sync(0xffffffffu, need)) break;
+      unsigned ind = 1;
+      double sn = 0.0, cs = 1.0;
+      bool drew = false;
+      if (need) {
+        ind = ws_uniform_int(ws, 1u, unsigned(nb - 2));
+        const unsigned cth = ws.c;
+        const unsigned w0 = ws_next(ws), w1 = ws_next(ws);
+        if (ws.underrun) {
+          dead = true;
+          ind = 1;
+        } else {
+          drew = true;
+          if (ws.philox) {
+            // uniform_real_distribution(0, 2*pi): canonical*(b-a)+a
+            const double th = canonical_words(w0, w1) * (2 * 3.14159265358979323846 - 0.0) + 0.0;
+            sincos(th, &sn, &cs);
+          } else {
+            sn = a.tape_sin[size_t(R.r) * a.tape_n + cth];
+            cs = a.tape_cos[size_t(R.r) * a.tape_n + cth];
+          }
+          attempts++;
+        }
       }
-      attempts++;
       // rodrigues_rotation, crankshaft.cc:11-73
       double dx = s.x[ind] - s.x[ind - 1];
       double dy = s.y[ind] - s.y[ind - 1];
@@ -856,59 +921,67 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
       const double Rzy = sn * kx + cth1 * ky * kz;
       const double Rzz = 1 + cth1 * (-ky * ky - kx * kx);
       const double px = s.x[ind], py = s.y[ind], pz = s.z[ind];
-      __syncwarp(gmask);
-      for (int k = lane; k < nb; k += G) {
-        if (k <= int(ind)) {
-          tx[k] = s.x[k];
-          ty[k] = s.y[k];
-          tz[k] = s.z[k];
-        } else {
-          double ox = s.x[k] - px, oy = s.y[k] - py, oz = s.z[k] - pz;
-          mindist3(a, ox, oy, oz);
-          double nx = Rxx * ox + Rxy * oy + Rxz * oz;
-          double ny = Ryx * ox + Ryy * oy + Ryz * oz;
-          double nz = Rzx * ox + Rzy * oy + Rzz * oz;
-          mindist3(a, nx, ny, nz);
-          tx[k] = px + nx;
-          ty[k] = py + ny;
-          tz[k] = pz + nz;
+      __syncwarp();
+      if (drew) {
+        for (int k = lane; k < nb; k += G) {
+          if (k <= int(ind)) {
+            tx[k] = s.x[k];
+            ty[k] = s.y[k];
+            tz[k] = s.z[k];
+          } else {
+            double ox = s.x[k] - px, oy = s.y[k] - py, oz = s.z[k] - pz;
+            mindist3(a, ox, oy, oz);
+            double nx = Rxx * ox + Rxy * oy + Rxz * oz;
+            double ny = Ryx * ox + Ryy * oy + Ryz * oz;
+            double nz = Rzx * ox + Rzy * oy + Rzz * oz;
+            mindist3(a, nx, ny, nz);
+            tx[k] = px + nx;
+            ty[k] = py + ny;
+            tz[k] = pz + nz;
+          }
         }
       }
-      __syncwarp(gmask);
-      ok = check_constraints<G>(a, R, tx, ty, tz, true, lane, gmask) == 3u;
-    } while (!ok);
-    if (ws.underrun) {
-      ws.c = start;
-      R.err |= HMC_ERR_TAPE_UNDERRUN;
-      break;
+      __syncwarp();
+      const bool good = check_constraints<G>(a, R, tx, ty, tz, true, lane, gmask) == 3u;
+      if (drew) ok = good;
     }
-    // config_int, crankshaft.cc:175-205: only transient-bond pairs can set bits
+    bool accept = false;
     unsigned long long trial = 0ull;
-    for (unsigned k = 0; k < R.tr->n_transient; k++) {
-      const int i = R.tr->tb_i[k], j = R.tr->tb_j[k];
-      const double d2 = dist2_ij(a, tx, ty, tz, i, j);
-      // first occurrence of a pair in the list owns it (std::find, config.h:34)
-      bool first = true;
-      for (unsigned q = 0; q < k; q++)
-        if (R.tr->tb_i[q] == i && R.tr->tb_j[q] == j) first = false;
-      if (first && !(d2 > R.rc2)) trial ^= (1ull << k);
-    }
-    // accept_move, crankshaft.cc:207-222
-    const double dS = R.sb[trial] - R.sb[R.config];
-    bool accept = true;
-    if (dS > 0) {
-      const unsigned w0 = ws_next(ws), w1 = ws_next(ws);
-      if (ws.underrun) {
+    if (dead) {
+      if (ws.c != start) { // roll the unfinished move back (positions untouched)
         ws.c = start;
         R.err |= HMC_ERR_TAPE_UNDERRUN;
-        break;
       }
-      const double u = canonical_words(w0, w1) * (1.0 - 0.0) + 0.0;
-      if (u > exp(-dS)) accept = false;
+    } else {
+      // config_int, crankshaft.cc:175-205: only transient-bond pairs can set bits
+      for (unsigned k = 0; k < R.tr->n_transient; k++) {
+        const int i = R.tr->tb_i[k], j = R.tr->tb_j[k];
+        const double d2 = dist2_ij(a, tx, ty, tz, i, j);
+        // first occurrence of a pair in the list owns it (std::find, config.h:34)
+        bool first = true;
+        for (unsigned q = 0; q < k; q++)
+          if (R.tr->tb_i[q] == i && R.tr->tb_j[q] == j) first = false;
+        if (first && !(d2 > R.rc2)) trial ^= (1ull << k);
+      }
+      // accept_move, crankshaft.cc:207-222
+      const double dS = R.sb[trial] - R.sb[R.config];
+      accept = true;
+      if (dS > 0) {
+        const unsigned w0 = ws_next(ws), w1 = ws_next(ws);
+        if (ws.underrun) {
+          ws.c = start;
+          R.err |= HMC_ERR_TAPE_UNDERRUN;
+          dead = true;
+          accept = false;
+        } else {
+          const double u = canonical_words(w0, w1) * (1.0 - 0.0) + 0.0;
+          if (u > exp(-dS)) accept = false;
+        }
+      }
     }
-    R.n_att += attempts;
+    if (!dead) R.n_att += attempts;
+    __syncwarp();
     if (accept) {
-      __syncwarp(gmask);
       for (int k = lane; k < nb; k += G) {
         s.x[k] = tx[k];
         s.y[k] = ty[k];
@@ -916,12 +989,14 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
       }
       R.config = trial;
       R.n_acc++;
-      __syncwarp(gmask);
     }
+    __syncwarp();
     // main.cc:232-236
-    const unsigned i = move_offset + mv;
-    for (unsigned j = 1; j < a.mc_write; j++)
-      if (i == (j * a.mc_moves) / a.mc_write) record_config_int(a, R, lane);
+    if (!dead) {
+      const unsigned i = move_offset + mv;
+      for (unsigned j = 1; j < a.mc_write; j++)
+        if (i == (j * a.mc_moves) / a.mc_write) record_config_int(a, R, lane);
+    }
   }
 }
 
@@ -931,7 +1006,7 @@ __device__ __forceinline__ double wl_gamma(const KArgs &a, unsigned iter_wl) {
   return iter_wl == 0 ? a.gamma0 : 1.0 / double(iter_wl); // main.cc:283,302-303
 }
 
-template <int G> __global__ void __launch_bounds__(128) hmc_ensemble_kernel(const __grid_constant__ KArgs a) {
+template <int G> __global__ void __launch_bounds__(128, HMC_MIN_BLOCKS) hmc_ensemble_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & (G - 1);
   const unsigned gmask = group_mask<G>();
@@ -939,11 +1014,17 @@ template <int G> __global__ void __launch_bounds__(128) hmc_ensemble_kernel(cons
   const Smem s = carve(smem_raw + size_t(group_in_cta) * a.smem_per_replica, a.nb, a.nslots);
   const int nb = a.nb;
 
+  constexpr int NG = 32 / G; // replica groups per warp, run in lockstep
+  const int group_in_warp = (threadIdx.x & 31) / G;
   for (;;) {
-    int r = 0;
-    if (lane == 0) r = int(atomicAdd(a.work_counter, 1u));
-    r = __shfl_sync(gmask, r, 0, G);
-    if (r >= a.n_replicas) break;
+    int r0 = 0;
+    if ((threadIdx.x & 31) == 0) r0 = int(atomicAdd(a.work_counter, unsigned(NG)));
+    r0 = __shfl_sync(0xffffffffu, r0, 0);
+    if (r0 >= a.n_replicas) break;
+    // a group past the end of the ensemble runs a clone of the last replica with all
+    // global side effects switched off, so the warp stays converged
+    const bool live = r0 + group_in_warp < a.n_replicas;
+    const int r = live ? r0 + group_in_warp : a.n_replicas - 1;
 
     Rep R;
     R.r = r;
@@ -961,6 +1042,7 @@ template <int G> __global__ void __launch_bounds__(128) hmc_ensemble_kernel(cons
     R.err = 0;
     R.n_coll = R.n_cell = R.n_att = R.n_acc = R.formed = R.broken = 0;
     R.tracing = (a.trace_cap != 0 && a.trace_replica == r);
+    R.live = live;
 
     // load the replica (bead clocks all equal t_now at a step boundary)
     for (int k = lane; k < nb; k += G) {
@@ -974,7 +1056,7 @@ template <int G> __global__ void __launch_bounds__(128) hmc_ensemble_kernel(cons
       s.vz[k] = v[2];
       s.tm[k] = a.t_now;
     }
-    __syncwarp(gmask);
+    __syncwarp();
 
     WordStream ws;
     ws.tape = a.tape_words ? a.tape_words + size_t(r) * a.tape_n : nullptr;
@@ -989,19 +1071,21 @@ template <int G> __global__ void __launch_bounds__(128) hmc_ensemble_kernel(cons
 
     bool vel_dirty = false; // velocity arrays hold crankshaft scratch
     auto save_vel = [&]() {
-      for (int k = lane; k < nb; k += G) {
-        double *v = a.vel + (size_t(r) * nb + k) * 3;
-        v[0] = s.vx[k];
-        v[1] = s.vy[k];
-        v[2] = s.vz[k];
+      if (live) {
+        for (int k = lane; k < nb; k += G) {
+          double *v = a.vel + (size_t(r) * nb + k) * 3;
+          v[0] = s.vx[k];
+          v[1] = s.vy[k];
+          v[2] = s.vz[k];
+        }
       }
-      __syncwarp(gmask);
+      __syncwarp();
     };
 
     if (a.op == HMC_OP_CRANK_ONLY) {
       crank_moves<G>(a, R, s, ws, a.move_offset, a.count, lane, gmask);
       vel_dirty = true;
-      if (lane == 0 && a.tape_consumed) a.tape_consumed[r] = ws.c;
+      if (lane == 0 && live && a.tape_consumed) a.tape_consumed[r] = ws.c;
     } else {
       unsigned long long draw = a.md_draw_base; // one draw index per initialize_system
       unsigned inj = 0;                          // injected-normals row
@@ -1027,12 +1111,12 @@ template <int G> __global__ void __launch_bounds__(128) hmc_ensemble_kernel(cons
               if (!(fabs(1 - (e1 / e0)) < 1e-6)) R.err |= HMC_ERR_ENERGY;
             }
             const double g = wl_gamma(a, iter_wl);
-            __syncwarp(gmask);
-            if (lane == 0) {
+            __syncwarp();
+            if (lane == 0 && live) {
               if (R.config == 0ull) R.sb[a.nstates - 1] -= g;
               else R.sb[a.nstates - 1] += g;
             }
-            __syncwarp(gmask);
+            __syncwarp();
           }
         } else {
           const unsigned nsteps = (a.phase == HMC_PHASE_EQ) ? a.nsteps_eq : a.nsteps;
@@ -1071,15 +1155,17 @@ template <int G> __global__ void __launch_bounds__(128) hmc_ensemble_kernel(cons
     }
 
     // store the replica back
-    __syncwarp(gmask);
-    for (int k = lane; k < nb; k += G) {
-      double *p = a.pos + (size_t(r) * nb + k) * 3;
-      p[0] = s.x[k];
-      p[1] = s.y[k];
-      p[2] = s.z[k];
+    __syncwarp();
+    if (live) {
+      for (int k = lane; k < nb; k += G) {
+        double *p = a.pos + (size_t(r) * nb + k) * 3;
+        p[0] = s.x[k];
+        p[1] = s.y[k];
+        p[2] = s.z[k];
+      }
     }
     if (!vel_dirty) save_vel();
-    if (lane == 0) {
+    if (lane == 0 && live) {
       a.config[r] = R.config;
       if (R.err) atomicOr(&a.err[r], R.err);
       const size_t base = size_t(a.n_trans) * a.nstates;
@@ -1091,7 +1177,7 @@ template <int G> __global__ void __launch_bounds__(128) hmc_ensemble_kernel(cons
       if (R.n_att) atomicAdd(&ev[2], R.n_att);
       if (R.n_acc) atomicAdd(&ev[3], R.n_acc);
     }
-    __syncwarp(gmask);
+    __syncwarp();
   }
 }
 
@@ -1107,9 +1193,12 @@ size_t hmc_smem_per_replica(int nb) {
 }
 
 int hmc_pick_group(int nb) {
-  // lanes per replica: enough that one pass of the partner loop covers most beads
-  if (nb <= 10) return 8;
-  if (nb <= 24) return 16;
+  // lanes per replica (measured on B200, profiles/README.md): the per-event work that
+  // every lane of a group repeats (argmin reduce, collision arithmetic, cell walls) is
+  // shared by 32/G replicas per warp, so small chains want narrow groups; from ~32
+  // beads on the partner loop dominates and a full warp per replica wins.
+  if (nb <= 24) return 8;
+  if (nb <= 32) return 16;
   return 32;
 }
 

@@ -48,7 +48,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("HMC_LIB") or LIB_PATH  # HMC_LIB: experimental variant
     if not os.path.exists(path):
         raise EngineError(
             "%s is missing: build it with `python -m hybridmc_b200.build` "
@@ -72,8 +72,7 @@ def load_library(path=None):
                  "hmc_get_dist", "hmc_get_config_int", "hmc_get_dist_hist",
                  "hmc_get_unique_config", "hmc_get_launch_stats", "hmc_counts_device_ptr"):
         getattr(lib, name).argtypes = None
-    if path == LIB_PATH:
-        _lib = lib
+    _lib = lib
     return lib
 
 
