@@ -172,7 +172,7 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.mc_draw_base = h->mc_draws;
   a.work_counter = h->d_work;
   a.smem_per_replica = uint32_t(hmc_smem_per_replica(h->nb));
-  a.max_events_per_step = 1u << 20; // ~100x the largest step of the shipped configs
+  a.max_events_per_step = 1u << 18; // ~30x the largest step of the shipped configs
 }
 
 int launch(hmc_handle h, const KArgs &a) {
@@ -539,6 +539,14 @@ int hmc_run(hmc_handle h, int phase, unsigned first_iter, unsigned n_iters) {
   if (phase < HMC_PHASE_EQ || phase > HMC_PHASE_MAIN) return fail(h, "hmc_run: bad phase");
   if (n_iters == 0) return 0;
   const hmc_params &p = h->params[0];
+  {
+    // the first step must not lie before the bead clocks: the reference would integrate
+    // backwards in time there (run_step, main.cc:104,135-138) and leave every well
+    const double first_t = phase == HMC_PHASE_WL ? double(first_iter * p.nsteps_wl) * p.del_t_wl
+                           : double(first_iter * (phase == HMC_PHASE_EQ ? p.nsteps_eq : p.nsteps)) * p.del_t;
+    if (first_t < h->t_now)
+      return fail(h, "hmc_run: step time before the bead clocks; call hmc_reset_clocks first");
+  }
   KArgs a;
   fill_kargs(h, a);
   a.op = HMC_OP_RUN;
@@ -573,6 +581,13 @@ int hmc_md_steps_injected(hmc_handle h, int phase, unsigned first_step, unsigned
   if (phase < HMC_PHASE_EQ || phase > HMC_PHASE_MAIN) return fail(h, "bad phase");
   if (nsteps == 0) return 0;
   const hmc_params &p = h->params[0];
+  {
+    const double first_t = phase == HMC_PHASE_WL
+                               ? double((first_step / unsigned(h->nstates)) * p.nsteps_wl) * p.del_t_wl
+                               : double(first_step) * p.del_t;
+    if (first_t < h->t_now)
+      return fail(h, "hmc_md_steps_injected: step time before the bead clocks; call hmc_reset_clocks first");
+  }
   const size_t n = size_t(h->R) * nsteps * h->nb * 3;
   CK(cudaSetDevice(h->device));
   if (n > h->normals_cap) {
@@ -621,7 +636,7 @@ int hmc_crankshaft_injected(hmc_handle h, unsigned move_offset, unsigned n_moves
     CK(cudaMalloc(reinterpret_cast<void **>(&h->d_tape_cos), n * sizeof(double)));
     h->tape_cap = n;
   }
-  if (!h->d_tape_consumed) CK(dalloc(&h->d_tape_consumed, size_t(h->R)));
+  if (!h->d_tape_consumed) CK(dalloc(&h->d_tape_consumed, 2 * size_t(h->R)));
   CK(cudaMemcpyAsync(h->d_tape_words, words, n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_tape_sin, sin_tab, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_tape_cos, cos_tab, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -642,6 +657,15 @@ int hmc_crankshaft_injected(hmc_handle h, unsigned move_offset, unsigned n_moves
   if (consumed)
     CK(cudaMemcpyAsync(consumed, h->d_tape_consumed, sizeof(uint32_t) * h->R, cudaMemcpyDeviceToHost,
                        h->stream));
+  return sync(h);
+}
+
+int hmc_get_moves_done(hmc_handle h, uint32_t *moves) {
+  if (!h || !moves) return fail(h, "hmc_get_moves_done: null");
+  if (!h->d_tape_consumed) return fail(h, "hmc_get_moves_done: no crankshaft call yet");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(moves, h->d_tape_consumed + h->R, sizeof(uint32_t) * h->R,
+                     cudaMemcpyDeviceToHost, h->stream));
   return sync(h);
 }
 

@@ -84,6 +84,11 @@ extern "C" {
 int hmc_init_pos_chain(const hmc_params *p, const uint32_t *seeds, unsigned n_seeds, double *pos) {
   std::seed_seq seq(seeds, seeds + n_seeds); // main.cc:379-380
   std::mt19937 mt(seq);
+  return hmc_init_pos_engine(p, &mt, pos);
+}
+
+int hmc_init_pos_engine(const hmc_params *p, void *engine, double *pos) {
+  std::mt19937 &mt = *static_cast<std::mt19937 *>(engine);
   const unsigned nb = p->nbeads;
   const double l = p->length, inv_l = 1.0 / l;
   const double nnear_min2 = p->nnear_min * p->nnear_min, nnear_max2 = p->nnear_max * p->nnear_max;

@@ -79,7 +79,7 @@ struct KArgs {
   const uint32_t *tape_words;
   const double *tape_sin, *tape_cos; // [R][tape_n]
   uint32_t tape_n;
-  uint32_t *tape_consumed; // [R]
+  uint32_t *tape_consumed; // [R] words used ++ [R] moves completed
   // work distribution
   unsigned int *work_counter;
   uint32_t smem_per_replica;

@@ -82,6 +82,7 @@ struct Rep {
   unsigned err;
   unsigned long long n_coll, n_cell, n_att, n_acc, formed, broken;
   bool tracing;
+  unsigned moves_done;
   bool live; // false: a clone filling an idle group of the warp; no global side effects
 };
 
@@ -993,6 +994,7 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
     __syncwarp();
     // main.cc:232-236
     if (!dead) {
+      R.moves_done++;
       const unsigned i = move_offset + mv;
       for (unsigned j = 1; j < a.mc_write; j++)
         if (i == (j * a.mc_moves) / a.mc_write) record_config_int(a, R, lane);
@@ -1041,6 +1043,7 @@ template <int G> __global__ void __launch_bounds__(128, HMC_MIN_BLOCKS) hmc_ense
     R.max_nbonds = R.tr->max_nbonds;
     R.err = 0;
     R.n_coll = R.n_cell = R.n_att = R.n_acc = R.formed = R.broken = 0;
+    R.moves_done = 0;
     R.tracing = (a.trace_cap != 0 && a.trace_replica == r);
     R.live = live;
 
@@ -1085,7 +1088,10 @@ template <int G> __global__ void __launch_bounds__(128, HMC_MIN_BLOCKS) hmc_ense
     if (a.op == HMC_OP_CRANK_ONLY) {
       crank_moves<G>(a, R, s, ws, a.move_offset, a.count, lane, gmask);
       vel_dirty = true;
-      if (lane == 0 && live && a.tape_consumed) a.tape_consumed[r] = ws.c;
+      if (lane == 0 && live && a.tape_consumed) {
+        a.tape_consumed[r] = ws.c;
+        a.tape_consumed[a.n_replicas + r] = R.moves_done;
+      }
     } else {
       unsigned long long draw = a.md_draw_base; // one draw index per initialize_system
       unsigned inj = 0;                          // injected-normals row

@@ -34,6 +34,7 @@ EXPORTS = [
     "hmc_get_config_int", "hmc_enable_dist_hist", "hmc_get_dist_hist",
     "hmc_get_unique_config", "hmc_enable_trace", "hmc_get_trace", "hmc_compute_entropy",
     "hmc_compute_g_val", "hmc_g_test", "hmc_wl_outer_iterations", "hmc_get_launch_stats", "hmc_init_pos_chain", "hmc_fp64_peak",
+    "hmc_get_moves_done", "hmc_init_pos_engine", "hmc_run_program_exact",
 ]
 
 _lib = None
@@ -330,3 +331,34 @@ def fp64_peak(device=0):
     if rc != 0:
         raise EngineError("hmc_fp64_peak failed (%d)" % rc)
     return a.value, b.value
+
+
+class ProgramResult(C.Structure):
+    _fields_ = [("s_bias", C.c_double * 16), ("config_count", C.c_uint64 * 16),
+                ("collisions", C.c_uint64), ("cell_crossings", C.c_uint64),
+                ("config_final", C.c_uint64), ("gtest_iters", C.c_uint32),
+                ("accepted", C.c_int), ("err_flags", C.c_uint32), ("pad", C.c_uint32),
+                ("seconds", C.c_double), ("pos_final", C.c_double * (64 * 3)),
+                ("message", C.c_char * 256)]
+
+
+def run_program_exact(params, device=0, pos_in=None, max_gtest_iters=0, dist_rows_cap=0):
+    """The reference program (src/main.cc:362-491) for one replica with the reference's
+    RNG contract std::mt19937(seed_seq(seeds)), trajectories on the GPU.
+    Returns (ProgramResult, dist[rows][n_nonlocal] or None)."""
+    lib = load_library()
+    res = ProgramResult()
+    pin = None
+    if pos_in is not None:
+        pin = np.ascontiguousarray(pos_in, dtype=np.float64)
+    dist = None
+    nrows = C.c_uint(0)
+    if dist_rows_cap:
+        dist = np.zeros((dist_rows_cap, max(params.n_nonlocal, 1)))
+    rc = lib.hmc_run_program_exact(C.byref(params), int(device), _p(pin) if pin is not None else None,
+                                   C.c_uint(max_gtest_iters), C.c_uint(dist_rows_cap),
+                                   _p(dist) if dist is not None else None, C.byref(nrows),
+                                   C.byref(res))
+    if rc != 0:
+        raise EngineError(res.message.decode() or "hmc_run_program_exact failed (%d)" % rc)
+    return res, (dist[:nrows.value] if dist is not None else None)

@@ -185,6 +185,10 @@ int hmc_crankshaft_injected(hmc_handle h, unsigned move_offset, unsigned n_moves
                             const double *cos_tab, unsigned n_words,
                             uint32_t *consumed);
 
+/* moves[R_total]: crankshaft moves completed by the last hmc_crankshaft_injected
+ * call (< n_moves when the tape ran out; the unfinished move is rolled back). */
+int hmc_get_moves_done(hmc_handle h, uint32_t *moves);
+
 /* ---- results ------------------------------------------------------------- */
 
 /* config_count[n_transitions][nstates] (pooled over replicas; only MD-step
@@ -249,6 +253,38 @@ unsigned hmc_wl_outer_iterations(const hmc_params *p);
  * "number of tries exceeded". */
 int hmc_init_pos_chain(const hmc_params *p, const uint32_t *seeds, unsigned n_seeds,
                        double *pos);
+
+/* Same with a caller-owned engine: `mt19937` points to a std::mt19937 that keeps
+ * its state across the call (C++ hosts only). */
+int hmc_init_pos_engine(const hmc_params *p, void *mt19937, double *pos);
+
+/* ---- whole program (host-side phase loop of main.cc:362-491) ------------------ */
+
+typedef struct hmc_program_result {
+  double s_bias[16];
+  uint64_t config_count[16]; /* last G-test iteration */
+  uint64_t collisions, cell_crossings;
+  uint64_t config_final;
+  uint32_t gtest_iters;
+  int accepted;
+  uint32_t err_flags;
+  uint32_t pad;
+  double seconds;
+  double pos_final[HMC_MAX_BEADS * 3];
+  char message[256];
+} hmc_program_result;
+
+/* The reference program for ONE replica with the reference's RNG contract,
+ * std::mt19937(std::seed_seq(p->seeds)): init_pos (or pos_in, the --input-file
+ * path), total_iter_eq equilibration iterations, Wang-Landau, then G-test
+ * iterations until acceptance or max_gtest_iters (0 = p->max_g_test_count).
+ * The host draws every variate with libstdc++ exactly as the reference does and
+ * injects it, so s_bias / counts / dist are bit-identical to the reference's.
+ * dist_out (optional): up to dist_rows_cap rows of n_nonlocal doubles. */
+int hmc_run_program_exact(const hmc_params *p, int device, const double *pos_in,
+                          unsigned max_gtest_iters, unsigned dist_rows_cap,
+                          double *dist_out, unsigned *n_dist_rows,
+                          hmc_program_result *res);
 
 /* Measured FP64 issue rate of `device` in TFLOP/s: DFMA chains, and DMUL+DADD
  * chains (the ceiling for this engine, which is compiled without FMA
