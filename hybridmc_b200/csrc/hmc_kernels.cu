@@ -37,7 +37,10 @@
 
 #include <math_constants.h>
 
-// register budget: 128 threads x HMC_MIN_BLOCKS CTAs per SM
+// register budget: HMC_BLOCK threads x HMC_MIN_BLOCKS CTAs per SM
+#ifndef HMC_BLOCK
+#define HMC_BLOCK 128
+#endif
 #ifndef HMC_MIN_BLOCKS
 #define HMC_MIN_BLOCKS 4
 #endif
@@ -46,29 +49,44 @@ namespace {
 
 // ----------------------------------------------------------------- helpers --
 
+// Shared-memory image of one replica.
+//   beads: array-of-structs, BSTRIDE doubles per bead: x y z vx vy vz clock cell(pack) - -
+//          one address computation per bead and four 128-bit loads fetch the whole
+//          record; a stride of 80 B keeps every quarter-warp of such loads conflict-free
+//          (20 k mod 32 covers all banks for 8 consecutive k).
+//   evt / evty: the event table (time, latched type) — nb cell slots then the pair slots.
+constexpr int BSTRIDE = 10;
+enum { F_X = 0, F_Y = 1, F_Z = 2, F_VX = 3, F_VY = 4, F_VZ = 5, F_T = 6, F_CELL = 7 };
+
 struct Smem {
-  double *x, *y, *z, *vx, *vy, *vz, *tm, *evt;
-  uint8_t *evty, *cx, *cy, *cz;
+  double *b;   // [nb][BSTRIDE]
+  double *evt; // [nslots]
+  uint8_t *evty;
+  const uint16_t *slot_row; // [nb]: slot(lo,hi) = slot_row[lo] + hi (CTA-shared)
+  int nb;
 };
 
-__device__ __forceinline__ Smem carve(unsigned char *base, int nb, int nslots) {
+__device__ __forceinline__ Smem carve(unsigned char *base, const uint16_t *slot_row, int nb,
+                                      int nslots) {
   Smem s;
   double *d = reinterpret_cast<double *>(base);
-  s.x = d;
-  s.y = d + nb;
-  s.z = d + 2 * nb;
-  s.vx = d + 3 * nb;
-  s.vy = d + 4 * nb;
-  s.vz = d + 5 * nb;
-  s.tm = d + 6 * nb;
-  s.evt = d + 7 * nb;
-  uint8_t *b = reinterpret_cast<uint8_t *>(d + 7 * nb + nslots);
-  s.evty = b;
-  s.cx = b + nslots;
-  s.cy = s.cx + nb;
-  s.cz = s.cy + nb;
+  s.b = d;
+  s.evt = d + BSTRIDE * nb;
+  s.evty = reinterpret_cast<uint8_t *>(d + BSTRIDE * nb + nslots);
+  s.slot_row = slot_row;
+  s.nb = nb;
   return s;
 }
+
+#define BX(s, k) ((s).b[BSTRIDE * (k) + F_X])
+#define BY(s, k) ((s).b[BSTRIDE * (k) + F_Y])
+#define BZ(s, k) ((s).b[BSTRIDE * (k) + F_Z])
+#define BVX(s, k) ((s).b[BSTRIDE * (k) + F_VX])
+#define BVY(s, k) ((s).b[BSTRIDE * (k) + F_VY])
+#define BVZ(s, k) ((s).b[BSTRIDE * (k) + F_VZ])
+#define BT(s, k) ((s).b[BSTRIDE * (k) + F_T])
+// packed cell index: x | y << 8 | z << 16
+#define BCELL(s, k) (reinterpret_cast<unsigned *>((s).b + BSTRIDE * (k) + F_CELL)[0])
 
 // per-replica register state (uniform across the lanes of a group)
 struct Rep {
@@ -132,14 +150,16 @@ struct Bead {
 };
 
 __device__ __forceinline__ Bead load_bead(const Smem &s, int k) {
+  const double2 *r = reinterpret_cast<const double2 *>(s.b + BSTRIDE * k);
+  const double2 a0 = r[0], a1 = r[1], a2 = r[2];
   Bead b;
-  b.x = s.x[k];
-  b.y = s.y[k];
-  b.z = s.z[k];
-  b.vx = s.vx[k];
-  b.vy = s.vy[k];
-  b.vz = s.vz[k];
-  b.t = s.tm[k];
+  b.x = a0.x;
+  b.y = a0.y;
+  b.z = a1.x;
+  b.vx = a1.y;
+  b.vy = a2.x;
+  b.vz = a2.y;
+  b.t = BT(s, k);
   return b;
 }
 
@@ -162,14 +182,17 @@ __device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, c
                                                  int p, int q, bool p_is_lo, int d,
                                                  unsigned info, bool want, double &tout) {
   // choose the roles by INDEX and load each bead once (no 64-bit selects)
-  const double tp = s.tm[p], tq = s.tm[q];
+  const double tp = BT(s, p), tq = BT(s, q);
   const bool sw = p_is_lo ? (tp < tq) : !(tq < tp); // true: "i" is q
   const int bi_ = sw ? q : p, bj_ = sw ? p : q;
   const double ti = sw ? tq : tp, tj = sw ? tp : tq;
-  const double xi = s.x[bi_], yi = s.y[bi_], zi = s.z[bi_];
-  const double xj = s.x[bj_], yj = s.y[bj_], zj = s.z[bj_];
-  const double vxi = s.vx[bi_], vyi = s.vy[bi_], vzi = s.vz[bi_];
-  const double vxj = s.vx[bj_], vyj = s.vy[bj_], vzj = s.vz[bj_];
+  // three 128-bit loads per bead
+  const double2 *ri = reinterpret_cast<const double2 *>(s.b + BSTRIDE * bi_);
+  const double2 *rj = reinterpret_cast<const double2 *>(s.b + BSTRIDE * bj_);
+  const double2 i0 = ri[0], i1 = ri[1], i2 = ri[2];
+  const double2 j0 = rj[0], j1 = rj[1], j2 = rj[2];
+  const double xi = i0.x, yi = i0.y, zi = i1.x, vxi = i1.y, vyi = i2.x, vzi = i2.y;
+  const double xj = j0.x, yj = j0.y, zj = j1.x, vxj = j1.y, vyj = j2.x, vzj = j2.y;
   const double dt = ti - tj;
   double dx = xj + vxj * dt - xi;
   double dy = yj + vyj * dt - yi;
@@ -270,11 +293,12 @@ __device__ __forceinline__ bool predict_cell(const KArgs &a, const Bead &b, int 
   return cr;
 }
 
-// cells within the 27-neighbourhood (periodic), valid for ncell >= 4
-__device__ __forceinline__ bool adj1(int ca, int cb, int nc) {
-  int d = ca - cb;
-  if (d < 0) d += nc;
-  return d == 0 || d == 1 || d == nc - 1;
+// Cell adjacency within the 27-neighbourhood (periodic; valid for ncell >= 4) for packed
+// cells (x | y<<8 | z<<16), all three axes at once with byte-SIMD:
+// per-axis |ca - cb| must be 0, 1 or nc-1.  Returns a byte mask (0xff per adjacent axis).
+__device__ __forceinline__ unsigned adj_mask(unsigned ca, unsigned cb, unsigned ncm1x3) {
+  const unsigned ad = __vabsdiffu4(ca, cb);
+  return __vcmpleu4(ad, 0x00010101u) | __vcmpeq4(ad, ncm1x3);
 }
 
 // -------------------------------------------------------------------- RNG --
@@ -376,9 +400,9 @@ __device__ __forceinline__ double hamiltonian(const KArgs &a, const Rep &R, cons
   double ke = 0.0;
   const double hm = 0.5 * a.m;
   for (int i = 0; i < a.nb; i++) {
-    const double vx2 = s.vx[i] * s.vx[i];
-    const double vy2 = s.vy[i] * s.vy[i];
-    const double vz2 = s.vz[i] * s.vz[i];
+    const double vx2 = BVX(s, i) * BVX(s, i);
+    const double vy2 = BVY(s, i) * BVY(s, i);
+    const double vz2 = BVZ(s, i) * BVZ(s, i);
     ke += hm * (vx2 + vy2 + vz2);
   }
   return ke + R.sb[R.config];
@@ -393,9 +417,11 @@ __device__ __forceinline__ bool check_bond_tol(double min2, double max2, double 
 }
 
 // min-image squared distance of beads i,j with the operand order pos[i]-pos[j]
-__device__ __forceinline__ double dist2_ij(const KArgs &a, const double *X, const double *Y,
-                                           const double *Z, int i, int j) {
-  double dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
+// P points at the first component of a coordinate triple inside the bead records
+// (positions: s.b + F_X, crankshaft trial coordinates: s.b + F_VX), stride BSTRIDE.
+__device__ __forceinline__ double dist2_ij(const KArgs &a, const double *P, int i, int j) {
+  const double *pi = P + BSTRIDE * i, *pj = P + BSTRIDE * j;
+  double dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
   mindist3(a, dx, dy, dz);
   return dx * dx + dy * dy + dz * dz;
 }
@@ -404,9 +430,8 @@ __device__ __forceinline__ double dist2_ij(const KArgs &a, const double *X, cons
 // (crankshaft.cc:88-123, strict) and check_nonlocal_dist (crankshaft.cc:125-171) over all
 // pairs, lane-parallel.  Returns bit0 = local ok, bit1 = nonlocal ok (group-uniform).
 template <int G>
-__device__ __forceinline__ unsigned check_constraints(const KArgs &a, const Rep &R, const double *X,
-                                                      const double *Y, const double *Z, bool strict,
-                                                      int lane, unsigned gmask) {
+__device__ __forceinline__ unsigned check_constraints(const KArgs &a, const Rep &R, const double *P,
+                                                      bool strict, int lane, unsigned gmask) {
   bool lok = true, nok = true;
   for (int p = lane; p < a.npairs; p += G) {
     const uchar2 ij = __ldg(&a.pair_ij[p]);
@@ -414,7 +439,8 @@ __device__ __forceinline__ unsigned check_constraints(const KArgs &a, const Rep 
     if (d <= 2) {
       // reference operand order here is pos[j]-pos[i]; dist2 is sign-symmetric
       // only after squaring, so keep the order
-      double dx = X[j] - X[i], dy = Y[j] - Y[i], dz = Z[j] - Z[i];
+      const double *pi = P + BSTRIDE * i, *pj = P + BSTRIDE * j;
+      double dx = pj[0] - pi[0], dy = pj[1] - pi[1], dz = pj[2] - pi[2];
       mindist3(a, dx, dy, dz);
       const double d2 = dx * dx + dy * dy + dz * dz;
       const double mn = d == 1 ? a.near_min2 : a.nnear_min2;
@@ -422,7 +448,7 @@ __device__ __forceinline__ unsigned check_constraints(const KArgs &a, const Rep 
       const bool ok = strict ? (d2 > mn && d2 < mx) : check_bond_tol(mn, mx, d2);
       lok = lok && ok;
     } else {
-      const double d2 = dist2_ij(a, X, Y, Z, i, j);
+      const double d2 = dist2_ij(a, P, i, j);
       const unsigned info = __ldg(&R.pinfo[p]);
       bool ok = d2 > a.rh2;
       if (info & 0x80u) {
@@ -444,13 +470,13 @@ template <int G>
 __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *normals,
                           unsigned long long draw, int lane, unsigned gmask) {
   const int nb = a.nb;
-  const unsigned ok = check_constraints<G>(a, R, s.x, s.y, s.z, false, lane, gmask);
+  const unsigned ok = check_constraints<G>(a, R, s.b + F_X, false, lane, gmask);
   if (!(ok & 1u)) R.err |= HMC_ERR_LOCAL_OVERLAP;
   if (!(ok & 2u)) R.err |= HMC_ERR_NONLOCAL_OVERLAP;
 
   // init_cells (hardspheres.cc:334-369) + raw velocity draws (init_vel :197-209)
   for (int k = lane; k < nb; k += G) {
-    double x = s.x[k], y = s.y[k], z = s.z[k];
+    double x = BX(s, k), y = BY(s, k), z = BZ(s, k);
     x -= floor(x * a.inv_l) * a.l; // Box::minpos
     y -= floor(y * a.inv_l) * a.l;
     z -= floor(z * a.inv_l) * a.l;
@@ -459,9 +485,7 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
     ix = min(max(ix, 0), hi);
     iy = min(max(iy, 0), hi);
     iz = min(max(iz, 0), hi);
-    s.cx[k] = uint8_t(ix);
-    s.cy[k] = uint8_t(iy);
-    s.cz[k] = uint8_t(iz);
+    BCELL(s, k) = unsigned(ix) | (unsigned(iy) << 8) | (unsigned(iz) << 16);
     double nx, ny, nz;
     if (a.rng_mode == HMC_RNG_INJECTED) {
       nx = normals[3 * k + 0];
@@ -485,25 +509,25 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
       ny = r0 * sn * a.vsigma;
       nz = r1 * cs1 * a.vsigma;
     }
-    s.vx[k] = nx;
-    s.vy[k] = ny;
-    s.vz[k] = nz;
+    BVX(s, k) = nx;
+    BVY(s, k) = ny;
+    BVZ(s, k) = nz;
   }
   __syncwarp();
 
   // shift_vel_CM_to_0 (hardspheres.cc:173-194): serial sums in bead order
   double tx = 0.0, ty = 0.0, tz = 0.0;
   for (int i = 0; i < nb; i++) {
-    tx += s.vx[i];
-    ty += s.vy[i];
-    tz += s.vz[i];
+    tx += BVX(s, i);
+    ty += BVY(s, i);
+    tz += BVZ(s, i);
   }
   const double cmx = tx / double(nb), cmy = ty / double(nb), cmz = tz / double(nb);
   __syncwarp();
   for (int k = lane; k < nb; k += G) {
-    s.vx[k] -= cmx;
-    s.vy[k] -= cmy;
-    s.vz[k] -= cmz;
+    BVX(s, k) -= cmx;
+    BVY(s, k) -= cmy;
+    BVZ(s, k) -= cmz;
   }
   __syncwarp();
 
@@ -512,7 +536,8 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
     const Bead b = load_bead(s, k);
     double t;
     unsigned wall = 0;
-    const bool cr = predict_cell(a, b, s.cx[k], s.cy[k], s.cz[k], t, wall);
+    const unsigned ck = BCELL(s, k);
+    const bool cr = predict_cell(a, b, int(ck & 0xffu), int((ck >> 8) & 0xffu), int(ck >> 16), t, wall);
     s.evt[k] = cr ? t : CUDART_INF;
     s.evty[k] = uint8_t(wall);
   }
@@ -524,8 +549,8 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
     unsigned ty = 0xffu;
     bool doit = true;
     if (d >= 3)
-      doit = adj1(s.cx[i], s.cx[j], a.ncell) && adj1(s.cy[i], s.cy[j], a.ncell) &&
-             adj1(s.cz[i], s.cz[j], a.ncell);
+      doit = (adj_mask(BCELL(s, i), BCELL(s, j), unsigned(a.ncell - 1) * 0x00010101u) &
+              0x00ffffffu) == 0x00ffffffu;
     if (doit) {
       double tt;
       ty = predict_pair(a, R, s, i, j, true, d, __ldg(&R.pinfo[p]), true, tt);
@@ -592,7 +617,8 @@ __device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_ti
     const unsigned wall = is_cell ? ty : 0u;
 
     Bead I = load_bead(s, bi), J = load_bead(s, bj);
-    int cxn = s.cx[bi], cyn = s.cy[bi], czn = s.cz[bi];
+    const unsigned ci0 = BCELL(s, bi);
+    int cxn = int(ci0 & 0xffu), cyn = int((ci0 >> 8) & 0xffu), czn = int(ci0 >> 16);
     // BeadCellEvent (hardspheres.cc:1622-1645): new cell from the wall latched at
     // prediction (t_until_cell :589-666)
     if (is_cell) {
@@ -668,24 +694,22 @@ __device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_ti
     if (!has) {
       // nothing to write
     } else if (lane == 0) {
-      s.x[bi] = I.x;
-      s.y[bi] = I.y;
-      s.z[bi] = I.z;
-      s.vx[bi] = I.vx;
-      s.vy[bi] = I.vy;
-      s.vz[bi] = I.vz;
-      s.tm[bi] = t;
-      s.cx[bi] = uint8_t(cxn);
-      s.cy[bi] = uint8_t(cyn);
-      s.cz[bi] = uint8_t(czn);
+      BX(s, bi) = I.x;
+      BY(s, bi) = I.y;
+      BZ(s, bi) = I.z;
+      BVX(s, bi) = I.vx;
+      BVY(s, bi) = I.vy;
+      BVZ(s, bi) = I.vz;
+      BT(s, bi) = t;
+      BCELL(s, bi) = unsigned(cxn) | (unsigned(cyn) << 8) | (unsigned(czn) << 16);
     } else if (lane == 1 && !is_cell) {
-      s.x[bj] = J.x;
-      s.y[bj] = J.y;
-      s.z[bj] = J.z;
-      s.vx[bj] = J.vx;
-      s.vy[bj] = J.vy;
-      s.vz[bj] = J.vz;
-      s.tm[bj] = t;
+      BX(s, bj) = J.x;
+      BY(s, bj) = J.y;
+      BZ(s, bj) = J.z;
+      BVX(s, bj) = J.vx;
+      BVY(s, bj) = J.vy;
+      BVZ(s, bj) = J.vz;
+      BT(s, bj) = t;
     }
     if (has) trace_event(a, R, lane, is_cell ? unsigned(HMC_EV_BEAD_CELL) : ty, bi, is_cell ? wall : bj, t);
     __syncwarp();
@@ -703,12 +727,11 @@ __device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_ti
       const int qb = lane >= 3 ? 1 : 0, ax = lane - 3 * qb; // lanes 0-2: bead bi, 3-5: bead bj
       const bool on = lane < 6;
       const int b = qb ? bj : bi;
-      const double *P = ax == 0 ? s.x : ax == 1 ? s.y : s.z;
-      const double *V = ax == 0 ? s.vx : ax == 1 ? s.vy : s.vz;
-      const uint8_t *Cc = ax == 0 ? s.cx : ax == 1 ? s.cy : s.cz;
-      const double v = on ? V[b] : 1.0;
-      const double pp = on ? P[b] : 0.0;
-      const double cc = on ? double(Cc[b]) : 0.0;
+      const double *rec = s.b + BSTRIDE * b;
+      const int axc = on ? ax : 0;
+      const double v = on ? rec[F_VX + axc] : 1.0;
+      const double pp = on ? rec[F_X + axc] : 0.0;
+      const double cc = on ? double((BCELL(s, b) >> (8 * axc)) & 0xffu) : 0.0;
       const double dd = mindist1(a, a.lcell * cc - pp);
       const double numer = v > 0 ? dd + a.lcell : dd;
       const double cand = numer / v;
@@ -734,7 +757,7 @@ __device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_ti
         cr = cr || t2;
         if (has && lane == 0 && q < nbead) {
           const int bq = q ? bj : bi;
-          s.evt[bq] = cr ? s.tm[bq] + dtc : CUDART_INF;
+          s.evt[bq] = cr ? BT(s, bq) + dtc : CUDART_INF;
           s.evty[bq] = uint8_t(w);
         }
       }
@@ -742,12 +765,13 @@ __device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_ti
 
     // partner predictions, both beads in one flattened lane loop
     {
-      const int axis = int(wall >> 1);
-      const int bcx0 = s.cx[bi], bcy0 = s.cy[bi], bcz0 = s.cz[bi];
-      const int bcx1 = s.cx[bj], bcy1 = s.cy[bj], bcz1 = s.cz[bj];
+      const unsigned axis = wall >> 1;
+      const unsigned cb0 = BCELL(s, bi), cb1 = BCELL(s, bj);
+      const unsigned ncm1x3 = unsigned(nc - 1) * 0x00010101u;
       // the cell coordinate that became adjacent through a crossing
-      int far = (axis == 0 ? bcx0 : axis == 1 ? bcy0 : bcz0) + ((wall & 1u) ? -1 : 1);
+      int far = int((cb0 >> (8 * axis)) & 0xffu) + ((wall & 1u) ? -1 : 1);
       far = far < 0 ? far + nc : (far >= nc ? far - nc : far);
+      const unsigned others = 0x00ffffffu & ~(0xffu << (8 * axis)); // the two other axes
       const int nitem = nbead * nb;
       // warp-uniform trip count: 2*nb unless every group of the warp has a crossing
       const int nloop = __any_sync(0xffffffffu, has && !is_cell) ? 2 * nb : nb;
@@ -758,18 +782,15 @@ __device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_ti
         int k = second ? idx - nb : idx;
         const bool in_range = idx < nitem;
         k = in_range ? k : b;
-        const int lo = min(b, k), hi = max(b, k), d = hi - lo;
-        const int slot = nb + (k == b ? 0 : pair_index(lo, hi, nb));
-        const int bcx = second ? bcx1 : bcx0, bcy = second ? bcy1 : bcy0,
-                  bcz = second ? bcz1 : bcz0;
-        const int kcx = s.cx[k], kcy = s.cy[k], kcz = s.cz[k];
-        const bool ax_ok = adj1(bcx, kcx, nc), ay_ok = adj1(bcy, kcy, nc),
-                   az_ok = adj1(bcz, kcz, nc);
-        const int kax = axis == 0 ? kcx : axis == 1 ? kcy : kcz;
+        const int d = abs(b - k);
+        // nb + pair index; an in-range dummy for k == b (never stored)
+        const int slot = k == b ? nb : int(s.slot_row[min(b, k)]) + max(b, k);
+        const unsigned cb = second ? cb1 : cb0, ck = BCELL(s, k);
+        const unsigned am = adj_mask(cb, ck, ncm1x3);
         // which (b,k) the reference predicts at this event
-        const bool want_cell = d >= 3 && kax == far && (axis == 0 || ax_ok) &&
-                               (axis == 1 || ay_ok) && (axis == 2 || az_ok);
-        const bool want_coll = d < 3 || (ax_ok && ay_ok && az_ok);
+        const bool want_cell = d >= 3 && int((ck >> (8 * axis)) & 0xffu) == far &&
+                               (am & others) == others;
+        const bool want_coll = d < 3 || (am & 0x00ffffffu) == 0x00ffffffu;
         const bool active = has && in_range && k != b;
         const bool doit = active && (is_cell ? want_cell : want_coll);
         double tt;
@@ -789,11 +810,11 @@ __device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_ti
   }
   // advance every bead to step_time (main.cc:135-138)
   for (int k = lane; k < nb; k += G) {
-    const double dt = step_time - s.tm[k];
-    s.x[k] += s.vx[k] * dt;
-    s.y[k] += s.vy[k] * dt;
-    s.z[k] += s.vz[k] * dt;
-    s.tm[k] = step_time;
+    const double dt = step_time - BT(s, k);
+    BX(s, k) += BVX(s, k) * dt;
+    BY(s, k) += BVY(s, k) * dt;
+    BZ(s, k) += BVZ(s, k) * dt;
+    BT(s, k) = step_time;
   }
   __syncwarp();
 }
@@ -818,7 +839,7 @@ __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step
     const unsigned nrow = a.dist_cap ? a.dist_n[R.r] : 0u;
     for (int k = lane; k < int(R.tr->n_nonlocal); k += G) {
       const int i = R.tr->nl_i[k], j = R.tr->nl_j[k];
-      const double d = sqrt(dist2_ij(a, s.x, s.y, s.z, i, j));
+      const double d = sqrt(dist2_ij(a, s.b + F_X, i, j));
       if (a.dist_cap && nrow < a.dist_cap && R.live)
         a.dist[(size_t(R.r) * a.dist_cap + nrow) * a.dist_stride + k] = d;
       if (a.hist_bins && R.live) {
@@ -844,12 +865,12 @@ __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step
       for (int k = lane; k < a.nb; k += G) {
         double *up = a.uniq_pos + (size_t(R.r) * a.nb + k) * 3;
         double *uv = a.uniq_vel + (size_t(R.r) * a.nb + k) * 3;
-        up[0] = s.x[k];
-        up[1] = s.y[k];
-        up[2] = s.z[k];
-        uv[0] = s.vx[k];
-        uv[1] = s.vy[k];
-        uv[2] = s.vz[k];
+        up[0] = BX(s, k);
+        up[1] = BY(s, k);
+        up[2] = BZ(s, k);
+        uv[0] = BVX(s, k);
+        uv[1] = BVY(s, k);
+        uv[2] = BVZ(s, k);
       }
       if (lane == 0) a.uniq_found[R.r] = 1;
     }
@@ -870,7 +891,6 @@ template <int G>
 __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &ws,
                             unsigned move_offset, unsigned n_moves, int lane, unsigned gmask) {
   const int nb = a.nb;
-  double *tx = s.vx, *ty = s.vy, *tz = s.vz;
   bool dead = false; // tape ran out: this group sits out the remaining moves
   for (unsigned mv = 0; mv < n_moves; mv++) {
     const unsigned start = ws.c;
@@ -905,9 +925,9 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
         }
       }
       // rodrigues_rotation, crankshaft.cc:11-73
-      double dx = s.x[ind] - s.x[ind - 1];
-      double dy = s.y[ind] - s.y[ind - 1];
-      double dz = s.z[ind] - s.z[ind - 1];
+      double dx = BX(s, ind) - BX(s, ind - 1);
+      double dy = BY(s, ind) - BY(s, ind - 1);
+      double dz = BZ(s, ind) - BZ(s, ind - 1);
       mindist3(a, dx, dy, dz);
       const double inv = 1 / sqrt(dx * dx + dy * dy + dz * dz);
       const double kx = dx * inv, ky = dy * inv, kz = dz * inv;
@@ -921,29 +941,29 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
       const double Rzx = -sn * ky + cth1 * kx * kz;
       const double Rzy = sn * kx + cth1 * ky * kz;
       const double Rzz = 1 + cth1 * (-ky * ky - kx * kx);
-      const double px = s.x[ind], py = s.y[ind], pz = s.z[ind];
+      const double px = BX(s, ind), py = BY(s, ind), pz = BZ(s, ind);
       __syncwarp();
       if (drew) {
         for (int k = lane; k < nb; k += G) {
           if (k <= int(ind)) {
-            tx[k] = s.x[k];
-            ty[k] = s.y[k];
-            tz[k] = s.z[k];
+            BVX(s, k) = BX(s, k);
+            BVY(s, k) = BY(s, k);
+            BVZ(s, k) = BZ(s, k);
           } else {
-            double ox = s.x[k] - px, oy = s.y[k] - py, oz = s.z[k] - pz;
+            double ox = BX(s, k) - px, oy = BY(s, k) - py, oz = BZ(s, k) - pz;
             mindist3(a, ox, oy, oz);
             double nx = Rxx * ox + Rxy * oy + Rxz * oz;
             double ny = Ryx * ox + Ryy * oy + Ryz * oz;
             double nz = Rzx * ox + Rzy * oy + Rzz * oz;
             mindist3(a, nx, ny, nz);
-            tx[k] = px + nx;
-            ty[k] = py + ny;
-            tz[k] = pz + nz;
+            BVX(s, k) = px + nx;
+            BVY(s, k) = py + ny;
+            BVZ(s, k) = pz + nz;
           }
         }
       }
       __syncwarp();
-      const bool good = check_constraints<G>(a, R, tx, ty, tz, true, lane, gmask) == 3u;
+      const bool good = check_constraints<G>(a, R, s.b + F_VX, true, lane, gmask) == 3u;
       if (drew) ok = good;
     }
     bool accept = false;
@@ -957,7 +977,7 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
       // config_int, crankshaft.cc:175-205: only transient-bond pairs can set bits
       for (unsigned k = 0; k < R.tr->n_transient; k++) {
         const int i = R.tr->tb_i[k], j = R.tr->tb_j[k];
-        const double d2 = dist2_ij(a, tx, ty, tz, i, j);
+        const double d2 = dist2_ij(a, s.b + F_VX, i, j);
         // first occurrence of a pair in the list owns it (std::find, config.h:34)
         bool first = true;
         for (unsigned q = 0; q < k; q++)
@@ -984,9 +1004,9 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
     __syncwarp();
     if (accept) {
       for (int k = lane; k < nb; k += G) {
-        s.x[k] = tx[k];
-        s.y[k] = ty[k];
-        s.z[k] = tz[k];
+        BX(s, k) = BVX(s, k);
+        BY(s, k) = BVY(s, k);
+        BZ(s, k) = BVZ(s, k);
       }
       R.config = trial;
       R.n_acc++;
@@ -1008,13 +1028,20 @@ __device__ __forceinline__ double wl_gamma(const KArgs &a, unsigned iter_wl) {
   return iter_wl == 0 ? a.gamma0 : 1.0 / double(iter_wl); // main.cc:283,302-303
 }
 
-template <int G> __global__ void __launch_bounds__(128, HMC_MIN_BLOCKS) hmc_ensemble_kernel(const __grid_constant__ KArgs a) {
+template <int G> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hmc_ensemble_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & (G - 1);
   const unsigned gmask = group_mask<G>();
   const int group_in_cta = threadIdx.x / G;
-  const Smem s = carve(smem_raw + size_t(group_in_cta) * a.smem_per_replica, a.nb, a.nslots);
   const int nb = a.nb;
+  // CTA-shared row offsets of the triangular pair table, behind the replica images:
+  // slot(lo,hi) = nb + pair_index(lo,hi) = slot_row[lo] + hi
+  uint16_t *slot_row =
+      reinterpret_cast<uint16_t *>(smem_raw + size_t(blockDim.x / G) * a.smem_per_replica);
+  for (int q = threadIdx.x; q < nb; q += blockDim.x)
+    slot_row[q] = uint16_t(nb + q * (2 * nb - q - 1) / 2 - q - 1);
+  __syncthreads();
+  const Smem s = carve(smem_raw + size_t(group_in_cta) * a.smem_per_replica, slot_row, nb, a.nslots);
 
   constexpr int NG = 32 / G; // replica groups per warp, run in lockstep
   const int group_in_warp = (threadIdx.x & 31) / G;
@@ -1050,14 +1077,14 @@ template <int G> __global__ void __launch_bounds__(128, HMC_MIN_BLOCKS) hmc_ense
     // load the replica (bead clocks all equal t_now at a step boundary)
     for (int k = lane; k < nb; k += G) {
       const double *p = a.pos + (size_t(r) * nb + k) * 3;
-      s.x[k] = p[0];
-      s.y[k] = p[1];
-      s.z[k] = p[2];
+      BX(s, k) = p[0];
+      BY(s, k) = p[1];
+      BZ(s, k) = p[2];
       const double *v = a.vel + (size_t(r) * nb + k) * 3;
-      s.vx[k] = v[0];
-      s.vy[k] = v[1];
-      s.vz[k] = v[2];
-      s.tm[k] = a.t_now;
+      BVX(s, k) = v[0];
+      BVY(s, k) = v[1];
+      BVZ(s, k) = v[2];
+      BT(s, k) = a.t_now;
     }
     __syncwarp();
 
@@ -1077,9 +1104,9 @@ template <int G> __global__ void __launch_bounds__(128, HMC_MIN_BLOCKS) hmc_ense
       if (live) {
         for (int k = lane; k < nb; k += G) {
           double *v = a.vel + (size_t(r) * nb + k) * 3;
-          v[0] = s.vx[k];
-          v[1] = s.vy[k];
-          v[2] = s.vz[k];
+          v[0] = BVX(s, k);
+          v[1] = BVY(s, k);
+          v[2] = BVZ(s, k);
         }
       }
       __syncwarp();
@@ -1165,9 +1192,9 @@ template <int G> __global__ void __launch_bounds__(128, HMC_MIN_BLOCKS) hmc_ense
     if (live) {
       for (int k = lane; k < nb; k += G) {
         double *p = a.pos + (size_t(r) * nb + k) * 3;
-        p[0] = s.x[k];
-        p[1] = s.y[k];
-        p[2] = s.z[k];
+        p[0] = BX(s, k);
+        p[1] = BY(s, k);
+        p[2] = BZ(s, k);
       }
     }
     if (!vel_dirty) save_vel();
@@ -1194,7 +1221,7 @@ template <int G> __global__ void __launch_bounds__(128, HMC_MIN_BLOCKS) hmc_ense
 size_t hmc_smem_per_replica(int nb) {
   const size_t npairs = size_t(nb) * (nb - 1) / 2;
   const size_t nslots = nb + npairs;
-  size_t bytes = 8 * (7 * size_t(nb) + nslots) + nslots + 3 * size_t(nb);
+  size_t bytes = 8 * (size_t(BSTRIDE) * nb + nslots) + nslots;
   return (bytes + 15) & ~size_t(15);
 }
 
@@ -1210,18 +1237,41 @@ int hmc_pick_group(int nb) {
 
 template <int G>
 static cudaError_t launch_g(const KArgs &a, cudaStream_t stream, int *grid_out, int *block_out) {
-  const int block = 128;
-  const int groups_per_cta = block / G;
-  const size_t smem = size_t(groups_per_cta) * a.smem_per_replica;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // CTA size: HMC_BLOCK threads, or half of it when shared memory (long chains) lets
+  // more warps stay resident that way
+  int block = HMC_BLOCK, per_sm = 0;
+  size_t smem = 0;
+  int best_warps = -1;
+  for (int cand = HMC_BLOCK; cand >= 64 && cand >= G; cand /= 2) {
+    const size_t sm = size_t(cand / G) * a.smem_per_replica +
+                      ((size_t(a.nb) * sizeof(uint16_t) + 15) & ~size_t(15));
+    cudaError_t e = cudaFuncSetAttribute(hmc_ensemble_kernel<G>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, hmc_ensemble_kernel<G>, cand, sm);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    if (n * cand / 32 > best_warps) {
+      best_warps = n * cand / 32;
+      block = cand;
+      per_sm = n;
+      smem = sm;
+    }
+  }
+  if (per_sm < 1) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(hmc_ensemble_kernel<G>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  int dev = 0, sms = 0, per_sm = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmc_ensemble_kernel<G>, block, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorInvalidConfiguration;
+  const int groups_per_cta = block / G;
   // persistent grid: a multiple of the SM count, never more CTAs than work
   long long need = (a.n_replicas + groups_per_cta - 1) / groups_per_cta;
   long long grid = (long long)sms * per_sm;
