@@ -172,6 +172,7 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.mc_draw_base = h->mc_draws;
   a.work_counter = h->d_work;
   a.smem_per_replica = uint32_t(hmc_smem_per_replica(h->nb));
+  a.short_chain = (double(h->nb - 1) * p.near_max < 1.45 * p.length) ? 1 : 0;
   a.max_events_per_step = 1u << 18; // ~30x the largest step of the shipped configs
 }
 

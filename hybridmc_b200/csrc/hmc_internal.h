@@ -84,6 +84,7 @@ struct KArgs {
   unsigned int *work_counter;
   uint32_t smem_per_replica;
   uint32_t max_events_per_step;
+  int short_chain; // (nb-1)*near_max < 1.45*length: bead-bead differences stay below 1.5 boxes
 };
 
 // launcher implemented in hmc_kernels.cu; group = lanes per replica (8/16/32)

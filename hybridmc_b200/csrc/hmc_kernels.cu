@@ -126,23 +126,28 @@ __device__ __forceinline__ double round_away(double x) {
   return (fabs(f) >= 0.5) ? r + copysign(1.0, x) : r;
 }
 
-// d - round(d/l)*l (Box::mindist, box.h:22-26).  For |d/l| < 1.5 — always, unless the
-// unwrapped chain is longer than 1.5 boxes — round() is 0 or +-1, so the product is
-// +-0 or +-l exactly and one compare + select + copysign replaces trunc/round/multiply;
-// the general form stays as a rarely taken branch.  Bit-identical either way.
+// d - round(d/l)*l (Box::mindist, box.h:22-26), general form: used for cell walls,
+// where the unwrapped coordinate may be many boxes away from the wall.
 __device__ __forceinline__ double mindist1(const KArgs &a, double d) {
+  return d - round_away(d * a.inv_l) * a.l;
+}
+
+// The same for a difference between two beads of the chain.  When the host has
+// checked that the fully stretched chain is shorter than 1.5 boxes (a.short_chain; true
+// for every shipped configuration) |d/l| < 1.5, so round() is 0 or +-1, the product is
+// +-0 or +-l exactly, and one compare + select + copysign replaces trunc/round/multiply.
+// Bit-identical to the general form; the branch is uniform across the launch.
+__device__ __forceinline__ double mindist_pair(const KArgs &a, double d) {
   const double t = d * a.inv_l;
-  const double at = fabs(t);
-  double corr = copysign(at >= 0.5 ? a.l : 0.0, t);
-  if (at >= 1.5) corr = round_away(t) * a.l;
-  return d - corr;
+  if (a.short_chain) return d - copysign(fabs(t) >= 0.5 ? a.l : 0.0, t);
+  return d - round_away(t) * a.l;
 }
 
 // Box::mindist, box.h:22-26
 __device__ __forceinline__ void mindist3(const KArgs &a, double &dx, double &dy, double &dz) {
-  dx = mindist1(a, dx);
-  dy = mindist1(a, dy);
-  dz = mindist1(a, dz);
+  dx = mindist_pair(a, dx);
+  dy = mindist_pair(a, dy);
+  dz = mindist_pair(a, dz);
 }
 
 struct Bead {
@@ -244,10 +249,10 @@ __device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, c
 // at rest (no event queued).
 __device__ __forceinline__ bool predict_cell(const KArgs &a, const Bead &b, int cx, int cy, int cz,
                                              double &tout, unsigned &wall) {
-  double dx = a.lcell * double(cx) - b.x;
-  double dy = a.lcell * double(cy) - b.y;
-  double dz = a.lcell * double(cz) - b.z;
-  mindist3(a, dx, dy, dz);
+  // general min-image: the unwrapped coordinate may be many boxes from the wall
+  const double dx = mindist1(a, a.lcell * double(cx) - b.x);
+  const double dy = mindist1(a, a.lcell * double(cy) - b.y);
+  const double dz = mindist1(a, a.lcell * double(cz) - b.z);
   bool cr = false;
   double dt = 0.0;
   if (b.vx > 0) {
