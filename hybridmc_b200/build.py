@@ -60,9 +60,29 @@ def build_library(force=False, verbose=False, out=None, defines=()):
     return out or LIB
 
 
+EXE = os.path.join(HERE, "hybridmc")
+
+
+def build_executable(force=False):
+    """The C++17 host executable (hybridmc_b200/hybridmc), linked against the library."""
+    src = os.path.join(CSRC, "host", "hybridmc_main.cpp")
+    deps = [src, os.path.join(CSRC, "host", "mini_json.h"), LIB] + HEADERS
+    if not force and os.path.exists(EXE) and all(
+            os.path.getmtime(d) <= os.path.getmtime(EXE) for d in deps if os.path.exists(d)):
+        return EXE
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", EXE, src, LIB, "-Wl,-rpath,$ORIGIN",
+           "-l:libstdc++.so.6"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return EXE
+
+
 if __name__ == "__main__":
     import sys
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv,
                         out=outs[0] if outs else None, defines=defs))
+    if not outs:
+        print(build_executable(force="--force" in sys.argv))

@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstring>
 #include <random>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -81,12 +82,41 @@ unsigned wl_iters(const hmc_params &p) { // main.cc:283-304
 
 } // namespace
 
+namespace {
+
+struct DistCollector { // sink used by the plain entry point
+  double *out;
+  unsigned cap, n, nbonds;
+};
+void collect_dist(void *user, const double *rows, unsigned nrows, unsigned nbonds) {
+  DistCollector *c = static_cast<DistCollector *>(user);
+  const unsigned take = std::min(nrows, c->cap - c->n);
+  std::memcpy(c->out + size_t(c->n) * nbonds, rows, sizeof(double) * size_t(take) * nbonds);
+  c->n += take;
+}
+
+} // namespace
+
 extern "C" {
 
 int hmc_run_program_exact(const hmc_params *p, int device, const double *pos_in,
                           unsigned max_gtest_iters, unsigned dist_rows_cap, double *dist_out,
                           unsigned *n_dist_rows, hmc_program_result *res) {
+  DistCollector c{dist_out, dist_rows_cap, 0, p ? p->n_nonlocal : 0};
+  hmc_sink sink{};
+  sink.user = &c;
+  if (dist_rows_cap && dist_out) sink.on_dist = collect_dist;
+  const int rc = hmc_run_program_exact_sink(p, device, pos_in, nullptr, max_gtest_iters, &sink, res);
+  if (n_dist_rows) *n_dist_rows = c.n;
+  return rc;
+}
+
+int hmc_run_program_exact_sink(const hmc_params *p, int device, const double *pos_in,
+                               const hmc_snapshot_in *snap, unsigned max_gtest_iters,
+                               const hmc_sink *sink, hmc_program_result *res) {
   if (!p || !res) return -1;
+  const hmc_sink no_sink{};
+  if (!sink) sink = &no_sink;
   std::memset(res, 0, sizeof *res);
   const unsigned nb = p->nbeads, ns = 1u << p->n_transient;
   if (ns > 16) {
@@ -106,7 +136,19 @@ int hmc_run_program_exact(const hmc_params *p, int device, const double *pos_in,
   const double vsig = std::sqrt(p->temp / p->m);
   std::vector<double> pos(3 * nb);
   // initialize_pos, main.cc:26-43
-  if (pos_in) std::memcpy(pos.data(), pos_in, sizeof(double) * 3 * nb);
+  std::vector<double> sb(ns);
+  for (unsigned i = 0; i < ns; i++) sb[i] = 3 * (p->n_transient - unsigned(__builtin_popcount(i)));
+  if (snap) { // read_snapshot, snapshot.cc:70-120
+    std::memcpy(pos.data(), snap->pos, sizeof(double) * 3 * nb);
+    std::memcpy(sb.data(), snap->s_bias, sizeof(double) * ns);
+    std::stringstream ss(snap->mt_state);
+    ss >> mt;
+    if (ss.fail()) {
+      std::snprintf(res->message, sizeof res->message, "snapshot: bad mt19937 state");
+      hmc_destroy(h);
+      return -6;
+    }
+  } else if (pos_in) std::memcpy(pos.data(), pos_in, sizeof(double) * 3 * nb);
   else if (hmc_init_pos_engine(p, &mt, pos.data()) != 0) {
     std::snprintf(res->message, sizeof res->message,
                   "number of tries exceeded while placing bead in box");
@@ -114,9 +156,10 @@ int hmc_run_program_exact(const hmc_params *p, int device, const double *pos_in,
     return -4;
   }
   RUN(hmc_set_positions(h, pos.data()));
-  if (pos_in) RUN(hmc_init_config_from_positions(h));
-  std::vector<double> sb(ns);
-  for (unsigned i = 0; i < ns; i++) sb[i] = 3 * (p->n_transient - unsigned(__builtin_popcount(i)));
+  if (snap) {
+    const uint64_t c = snap->config;
+    RUN(hmc_set_config(h, &c));
+  } else if (pos_in) RUN(hmc_init_config_from_positions(h));
   RUN(hmc_set_s_bias(h, sb.data(), int(ns))); // init_s, entropy.cc:14-20
   const auto t0 = std::chrono::steady_clock::now();
 
@@ -143,12 +186,19 @@ int hmc_run_program_exact(const hmc_params *p, int device, const double *pos_in,
     if (ntraj) RUN(hmc_md_steps_injected(h, HMC_PHASE_WL, 0, ntraj, normals.data()));
   }
   RUN(hmc_get_s_bias(h, sb.data(), int(ns)));
-  if (dist_rows_cap) RUN(hmc_enable_samples(h, dist_rows_cap, 0));
+  // per-iteration sample buffers: one dist row per MD step; config/int gets one entry
+  // per recorded MD step plus mc_write-1 per block of crankshaft moves
+  const unsigned dist_cap = sink->on_dist ? p->total_iter * p->nsteps : 0;
+  const unsigned cfg_cap =
+      sink->on_config_int
+          ? p->total_iter * p->nsteps / p->write_step + 2 + p->total_iter * p->mc_write
+          : 0;
+  if (dist_cap || cfg_cap) RUN(hmc_enable_samples(h, dist_cap, cfg_cap));
+  bool unique_sent = false;
 
   // the G-test loop, main.cc:451-491
   const unsigned cap = max_gtest_iters ? max_gtest_iters : p->max_g_test_count;
   unsigned gcount = 0;
-  uint32_t dist_total = 0;
   int accepted = 0;
   std::vector<uint64_t> cc(ns);
   std::vector<double> normals(size_t(p->nsteps) * 3 * nb);
@@ -181,21 +231,43 @@ int hmc_run_program_exact(const hmc_params *p, int device, const double *pos_in,
       }
     }
     RUN(hmc_get_counts(h, cc.data(), int(ns), nullptr, nullptr, nullptr));
-    if (dist_rows_cap && dist_out) { // DistWriter appends one row per MD step (main.cc:199-200)
-      std::vector<double> rows(size_t(dist_rows_cap) * std::max(1u, p->n_nonlocal));
+    if (dist_cap) { // DistWriter appends one row per MD step (main.cc:199-200)
+      std::vector<double> rows(size_t(dist_cap) * std::max(1u, p->n_nonlocal));
       uint32_t n = 0;
       RUN(hmc_get_dist(h, rows.data(), &n));
-      n = std::min<uint32_t>(n, dist_rows_cap);
-      const uint32_t room = dist_rows_cap - dist_total;
-      const uint32_t take = std::min(n, room);
-      std::memcpy(dist_out + size_t(dist_total) * p->n_nonlocal, rows.data(),
-                  sizeof(double) * size_t(take) * p->n_nonlocal);
-      dist_total += take;
+      sink->on_dist(sink->user, rows.data(), std::min<uint32_t>(n, dist_cap), p->n_nonlocal);
+    }
+    if (cfg_cap) {
+      std::vector<uint64_t> ci(cfg_cap);
+      uint32_t n = 0;
+      RUN(hmc_get_config_int(h, ci.data(), &n));
+      sink->on_config_int(sink->user, ci.data(), std::min<uint32_t>(n, cfg_cap));
+    }
+    if (sink->on_unique && !unique_sent) {
+      std::vector<double> up(3 * nb), uv(3 * nb);
+      uint8_t found = 0;
+      RUN(hmc_get_unique_config(h, up.data(), uv.data(), &found));
+      if (found) {
+        sink->on_unique(sink->user, up.data(), uv.data(), 1, nb);
+        unique_sent = true;
+      }
     }
     hmc_compute_entropy(cc.data(), sb.data(), int(ns), p->pos_scale, p->neg_scale);
     RUN(hmc_set_s_bias(h, sb.data(), int(ns)));
     gcount++;
-    accepted = hmc_g_test(cc.data(), int(ns), p->sig_level, nullptr, nullptr, nullptr);
+    double gv = 0, gc = 0, pv = 0;
+    accepted = hmc_g_test(cc.data(), int(ns), p->sig_level, &gv, &gc, &pv);
+    if (sink->on_round)
+      sink->on_round(sink->user, gcount - 1, cc.data(), sb.data(), int(ns), accepted, gv, gc, pv);
+    if (sink->on_snapshot) {
+      std::vector<double> cur(3 * nb);
+      uint64_t cfg = 0;
+      RUN(hmc_get_positions(h, cur.data()));
+      RUN(hmc_get_config(h, &cfg));
+      std::stringstream ss;
+      ss << mt;
+      sink->on_snapshot(sink->user, cur.data(), sb.data(), int(ns), cfg, ss.str().c_str());
+    }
   } while (gcount < cap && !accepted);
 
   res->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -216,7 +288,6 @@ int hmc_run_program_exact(const hmc_params *p, int device, const double *pos_in,
   uint64_t cfg = 0;
   RUN(hmc_get_config(h, &cfg));
   res->config_final = cfg;
-  if (n_dist_rows) *n_dist_rows = dist_total;
   hmc_destroy(h);
   return 0;
 }

@@ -35,6 +35,7 @@ EXPORTS = [
     "hmc_get_unique_config", "hmc_enable_trace", "hmc_get_trace", "hmc_compute_entropy",
     "hmc_compute_g_val", "hmc_g_test", "hmc_wl_outer_iterations", "hmc_get_launch_stats", "hmc_init_pos_chain", "hmc_fp64_peak",
     "hmc_get_moves_done", "hmc_init_pos_engine", "hmc_run_program_exact",
+    "hmc_run_program_exact_sink",
 ]
 
 _lib = None

@@ -286,6 +286,42 @@ int hmc_run_program_exact(const hmc_params *p, int device, const double *pos_in,
                           double *dist_out, unsigned *n_dist_rows,
                           hmc_program_result *res);
 
+/* Output hooks for a host program that writes the reference's datasets
+ * (src/main.cc:383-409,443-446,477-495).  Any pointer may be NULL. */
+typedef struct hmc_sink {
+  void *user;
+  /* once per G-test iteration: config_count row, updated s_bias, G-test verdict
+   * (main.cc:471-491; g_test prints the same numbers, entropy.cc:106-113) */
+  void (*on_round)(void *user, unsigned round, const uint64_t *config_count,
+                   const double *s_bias, int nstates, int accepted, double g_val,
+                   double g_crit, double p_val);
+  /* dist rows of that iteration, one per MD step (DistWriter, main.cc:199-200) */
+  void (*on_dist)(void *user, const double *rows, unsigned nrows, unsigned nbonds);
+  /* config/int entries of that iteration in append order (main.cc:205,234,245) */
+  void (*on_config_int)(void *user, const uint64_t *config_int, unsigned n);
+  /* unique_config/{pos,vel,config}: first recorded config == 1 (main.cc:211-216) */
+  void (*on_unique)(void *user, const double *pos, const double *vel, uint64_t config,
+                    unsigned nbeads);
+  /* snapshot point after every G-test iteration (main.cc:480-486): textual
+   * std::mt19937 state as written by operator<< (snapshot.cc:43-51) */
+  void (*on_snapshot)(void *user, const double *pos, const double *s_bias, int nstates,
+                      uint64_t config, const char *mt_state);
+} hmc_sink;
+
+/* Optional restart state (read_snapshot, src/snapshot.cc:70-120). */
+typedef struct hmc_snapshot_in {
+  const double *pos;     /* [nbeads][3] */
+  const double *s_bias;  /* [nstates] */
+  const char *mt_state;  /* textual std::mt19937 state */
+  uint64_t config;
+} hmc_snapshot_in;
+
+/* hmc_run_program_exact with output hooks and an optional snapshot to resume from
+ * (snap overrides pos_in, as initialize_pos does, main.cc:31-34). */
+int hmc_run_program_exact_sink(const hmc_params *p, int device, const double *pos_in,
+                               const hmc_snapshot_in *snap, unsigned max_gtest_iters,
+                               const hmc_sink *sink, hmc_program_result *res);
+
 /* Measured FP64 issue rate of `device` in TFLOP/s: DFMA chains, and DMUL+DADD
  * chains (the ceiling for this engine, which is compiled without FMA
  * contraction for bit parity).  Roofline denominator for bench.py. */
