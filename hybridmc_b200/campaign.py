@@ -130,3 +130,42 @@ def run_transition_ensemble(params_list, start_pos, replicas, device=0, seed=(1,
         if hist_bins:
             out["dist_hist"] = e.get_dist_hist()
         return out
+
+
+# ---- multi-GPU: one process per GPU, shard + one all-reduce per G-test round ----------
+
+def shard(n_items, rank, world):
+    """Round-robin assignment of the independent units (transitions of a layer, or replica
+    blocks of one transition) to ranks: rank r owns items r, r+world, ..."""
+    return list(range(rank, n_items, world))
+
+
+def allreduce_counts(counts):
+    """Sum the per-state counts `counts` (integer array, any shape) over all ranks of the
+    default torch.distributed group.  Integer sums are exact and order-independent, so
+    every rank then computes the identical s_bias update redundantly (no broadcast).
+    Works on CPU (gloo) and on a device accumulator view (nccl)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return counts
+    if isinstance(counts, torch.Tensor):
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        return counts
+    t = torch.from_numpy(np.ascontiguousarray(counts).astype(np.int64))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.numpy().astype(np.uint64).reshape(np.shape(counts))
+
+
+def pooled_round(local_counts, s_bias, p):
+    """One G-test round of the phase loop on pooled counts (main.cc:471-491):
+    all-reduce, compute_entropy, g_test.  Returns (s_bias, accepted, pooled_counts)."""
+    pooled = allreduce_counts(np.asarray(local_counts, dtype=np.uint64))
+    out = np.array(s_bias, dtype=np.float64).reshape(pooled.shape)
+    acc = np.zeros(len(pooled), dtype=bool) if pooled.ndim == 2 else None
+    if pooled.ndim == 1:
+        return compute_entropy(pooled, out, p.pos_scale, p.neg_scale), g_test(pooled, p.sig_level)[0], pooled
+    for t in range(len(pooled)):
+        out[t] = compute_entropy(pooled[t], out[t], p.pos_scale, p.neg_scale)
+        acc[t] = g_test(pooled[t], p.sig_level)[0]
+    return out, acc, pooled
