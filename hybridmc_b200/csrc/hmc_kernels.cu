@@ -113,9 +113,6 @@ template <int G> __device__ __forceinline__ unsigned group_mask() {
   }
 }
 
-__device__ __forceinline__ int pair_index(int i, int j, int nb) {
-  return i * (2 * nb - i - 1) / 2 + (j - i - 1);
-}
 
 // std::round (half away from zero), exact for every finite x: x - trunc(x) is exact,
 // so the comparison with 0.5 sees the true fraction.  5 instructions instead of the
@@ -210,30 +207,44 @@ __device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, c
   const double rv2 = rv * rv;
   const bool approaching = rv < 0;
   const bool local = d <= 2, near = d == 1;
-  // nonlocal bond bookkeeping (info == 0 for local pairs)
-  const unsigned tb = info & 0x7fu;
-  const bool perm = (info & 0x80u) != 0;
-  const unsigned long long tmask = tb ? (1ull << (tb - 1)) : 0ull;
-  const bool bonded_t = (R.config & tmask) != 0;
-  const bool nonbonded_t = (~R.config & tmask) != 0;
-  // get_rc2_inner / get_rc2_outer, hardspheres.cc:394-419
-  const double r2i = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
-  double r2o = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
-  r2o = (R.has_stair && nonbonded_t) ? R.stair2 : r2o;
-  const bool capcand = tmask && (unsigned(__popcll(R.config)) < R.max_nbonds) && nonbonded_t;
-  // first inner candidate: well minimum (local) / bond radius (capture) / hard core
-  const double s_in1 = local ? (near ? a.near_min2 : a.nnear_min2) : (capcand ? r2i : a.rh2);
-  const bool hit1 = approaching && (rv2 > vv * (rr - s_in1)); // t_until_inner_coll :217-240
-  // a failed capture falls through to the hard core (if_coll :457-467)
-  const bool hit2 = !local && capcand && !hit1 && approaching && (rv2 > vv * (rr - a.rh2));
-  const bool inner = hit1 || hit2;
-  const double s_out = local ? (near ? a.near_max2 : a.nnear_max2) : r2o;
-  const double s2 = hit1 ? s_in1 : (hit2 ? a.rh2 : s_out);
-  const bool outer_ok = local || bonded_t || perm || (R.has_stair && nonbonded_t);
+  bool inner, outer_ok;
+  double s2;
   unsigned ty;
-  if (local) ty = (near ? HMC_EV_MIN_NEAREST : HMC_EV_MIN_NNEAREST) + (inner ? 0u : 1u);
-  else ty = hit1 ? (capcand ? HMC_EV_MAX_NONLOCAL_INNER : HMC_EV_MIN_NONLOCAL_INNER)
-                 : (hit2 ? HMC_EV_MIN_NONLOCAL_INNER : HMC_EV_MAX_NONLOCAL_OUTER);
+  // (warp-uniform branch: every lane of the warp calls predict_pair together)
+  if (!__any_sync(0xffffffffu, info != 0u)) {
+    // no bonded / bondable pair among the 32 pairs of this pass — the common case:
+    // local wells and plain hard cores only
+    const double s_in = local ? (near ? a.near_min2 : a.nnear_min2) : a.rh2;
+    inner = approaching && (rv2 > vv * (rr - s_in)); // t_until_inner_coll :217-240
+    s2 = inner ? s_in : (near ? a.near_max2 : a.nnear_max2);
+    outer_ok = local;
+    ty = local ? (near ? HMC_EV_MIN_NEAREST : HMC_EV_MIN_NNEAREST) + (inner ? 0u : 1u)
+               : unsigned(HMC_EV_MIN_NONLOCAL_INNER);
+  } else {
+    // nonlocal bond bookkeeping (info == 0 for local pairs)
+    const unsigned tb = info & 0x7fu;
+    const bool perm = (info & 0x80u) != 0;
+    const unsigned long long tmask = tb ? (1ull << (tb - 1)) : 0ull;
+    const bool bonded_t = (R.config & tmask) != 0;
+    const bool nonbonded_t = (~R.config & tmask) != 0;
+    // get_rc2_inner / get_rc2_outer, hardspheres.cc:394-419
+    const double r2i = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
+    double r2o = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
+    r2o = (R.has_stair && nonbonded_t) ? R.stair2 : r2o;
+    const bool capcand = tmask && (unsigned(__popcll(R.config)) < R.max_nbonds) && nonbonded_t;
+    // first inner candidate: well minimum (local) / bond radius (capture) / hard core
+    const double s_in1 = local ? (near ? a.near_min2 : a.nnear_min2) : (capcand ? r2i : a.rh2);
+    const bool hit1 = approaching && (rv2 > vv * (rr - s_in1)); // t_until_inner_coll :217-240
+    // a failed capture falls through to the hard core (if_coll :457-467)
+    const bool hit2 = !local && capcand && !hit1 && approaching && (rv2 > vv * (rr - a.rh2));
+    inner = hit1 || hit2;
+    const double s_out = local ? (near ? a.near_max2 : a.nnear_max2) : r2o;
+    s2 = hit1 ? s_in1 : (hit2 ? a.rh2 : s_out);
+    outer_ok = local || bonded_t || perm || (R.has_stair && nonbonded_t);
+    if (local) ty = (near ? HMC_EV_MIN_NEAREST : HMC_EV_MIN_NNEAREST) + (inner ? 0u : 1u);
+    else ty = hit1 ? (capcand ? HMC_EV_MAX_NONLOCAL_INNER : HMC_EV_MIN_NONLOCAL_INNER)
+                   : (hit2 ? HMC_EV_MIN_NONLOCAL_INNER : HMC_EV_MAX_NONLOCAL_OUTER);
+  }
   // Lanes whose result is not needed (pair not predicted by the reference, or no event)
   // get harmless operands: a negative radicand or a NaN/zero dividend would send the
   // whole warp through the slow-path subroutines of sqrt / division.
@@ -547,22 +558,21 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
     s.evty[k] = uint8_t(wall);
   }
   // init_nearest/nnearest_bond_events (:885-937) and add_events_for_all_beads (:540-555)
-  for (int p = lane; p < a.npairs; p += G) {
+  for (int base = 0; base < a.npairs; base += G) {
+    const int p = min(base + lane, a.npairs - 1); // every lane calls predict_pair
+    const bool mine = base + lane < a.npairs;
     const uchar2 ij = __ldg(&a.pair_ij[p]);
     const int i = ij.x, j = ij.y, d = j - i;
-    double t = CUDART_INF;
-    unsigned ty = 0xffu;
-    bool doit = true;
+    bool doit = mine;
     if (d >= 3)
-      doit = (adj_mask(BCELL(s, i), BCELL(s, j), unsigned(a.ncell - 1) * 0x00010101u) &
-              0x00ffffffu) == 0x00ffffffu;
-    if (doit) {
-      double tt;
-      ty = predict_pair(a, R, s, i, j, true, d, __ldg(&R.pinfo[p]), true, tt);
-      if (ty != 0xffu) t = tt;
+      doit = mine && (adj_mask(BCELL(s, i), BCELL(s, j), unsigned(a.ncell - 1) * 0x00010101u) &
+                      0x00ffffffu) == 0x00ffffffu;
+    double tt;
+    const unsigned ty = predict_pair(a, R, s, i, j, true, d, __ldg(&R.pinfo[p]), doit, tt);
+    if (mine) {
+      s.evt[nb + p] = (ty != 0xffu) ? tt : CUDART_INF;
+      s.evty[nb + p] = uint8_t(ty);
     }
-    s.evt[nb + p] = t;
-    s.evty[nb + p] = uint8_t(ty);
   }
   __syncwarp();
 }
