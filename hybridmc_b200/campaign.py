@@ -125,8 +125,13 @@ def run_transition_ensemble(params_list, start_pos, replicas, device=0, seed=(1,
             e.set_s_bias(s_bias)
             if done.all():
                 break
+        upos, uvel, found = e.get_unique_config()
+        found = found.reshape(T, replicas).astype(bool)
+        upos = upos.reshape(T, replicas, e.nb, 3)
+        unique = [upos[t, np.nonzero(found[t])[0][0]].copy() if found[t].any() else None
+                  for t in range(T)]
         out = dict(s_bias=s_bias, rounds=rounds, counts=counts, events=e.get_event_counts(),
-                   err=err, accepted=done)
+                   err=err, accepted=done, unique_pos=unique, formed=formed, broken=broken)
         if hist_bins:
             out["dist_hist"] = e.get_dist_hist()
         return out

@@ -517,10 +517,8 @@ int hmc_reset_counts(hmc_handle h) {
                      h->stream));
   if (h->d_dist_n) CK(cudaMemsetAsync(h->d_dist_n, 0, sizeof(uint32_t) * h->R, h->stream));
   if (h->d_cfg_n) CK(cudaMemsetAsync(h->d_cfg_n, 0, sizeof(uint32_t) * h->R, h->stream));
-  if (h->d_hist)
-    CK(cudaMemsetAsync(h->d_hist, 0,
-                       sizeof(unsigned long long) * size_t(h->T) * h->n_nonlocal_max * h->hist_bins,
-                       h->stream));
+  // distance histograms keep accumulating over rounds, like the reference's `dist`
+  // dataset; hmc_enable_dist_hist re-zeroes them
   return sync(h);
 }
 
@@ -774,7 +772,7 @@ int hmc_enable_dist_hist(hmc_handle h, unsigned nbins, double rmax) {
   if (nbins) {
     if (!(rmax > 0)) return fail(h, "hmc_enable_dist_hist: rmax must be > 0");
     const size_t stride = h->n_nonlocal_max ? h->n_nonlocal_max : 1;
-    CK(dalloc(&h->d_hist, size_t(h->T) * stride * nbins));
+    CK(dalloc(&h->d_hist, size_t(h->T) * stride * 2 * nbins));
     h->hist_bins = nbins;
     h->hist_rmax = rmax;
   }
@@ -786,7 +784,7 @@ int hmc_get_dist_hist(hmc_handle h, uint64_t *hist) {
   if (!h->hist_bins) return fail(h, "hmc_get_dist_hist: histogram not enabled");
   const size_t stride = h->n_nonlocal_max ? h->n_nonlocal_max : 1;
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(hist, h->d_hist, sizeof(uint64_t) * size_t(h->T) * stride * h->hist_bins,
+  CK(cudaMemcpyAsync(hist, h->d_hist, sizeof(uint64_t) * size_t(h->T) * stride * 2 * h->hist_bins,
                      cudaMemcpyDeviceToHost, h->stream));
   return sync(h);
 }

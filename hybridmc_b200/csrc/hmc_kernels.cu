@@ -852,6 +852,11 @@ __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step
   // dist_between_nonlocal_beads (hardspheres.cc:1084-1104)
   if (a.dist_cap || a.hist_bins) {
     const unsigned nrow = a.dist_cap ? a.dist_n[R.r] : 0u;
+    // the histograms are split by the state of the first transient bond, r_t < rc, the
+    // split tools/mfpt.py applies to the dist rows (mfpt.py:104-125)
+    int on = 0;
+    if (a.hist_bins && R.tr->n_transient)
+      on = dist2_ij(a, s.b + F_X, R.tr->tb_i[0], R.tr->tb_j[0]) < R.rc2 ? 1 : 0;
     for (int k = lane; k < int(R.tr->n_nonlocal); k += G) {
       const int i = R.tr->nl_i[k], j = R.tr->nl_j[k];
       const double d = sqrt(dist2_ij(a, s.b + F_X, i, j));
@@ -860,7 +865,7 @@ __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step
       if (a.hist_bins && R.live) {
         int bin = int(d * a.hist_scale);
         bin = min(max(bin, 0), int(a.hist_bins) - 1);
-        atomicAdd(&a.hist[(size_t(trans) * a.dist_stride + k) * a.hist_bins + bin], 1ull);
+        atomicAdd(&a.hist[((size_t(trans) * a.dist_stride + k) * 2 + on) * a.hist_bins + bin], 1ull);
       }
     }
     __syncwarp();

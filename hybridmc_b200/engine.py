@@ -254,7 +254,7 @@ class Engine:
         self._hist_bins = nbins
 
     def get_dist_hist(self):
-        out = np.zeros((self.T, max(self.n_nonlocal, 1), self._hist_bins), dtype=np.uint64)
+        out = np.zeros((self.T, max(self.n_nonlocal, 1), 2, self._hist_bins), dtype=np.uint64)
         self._ck(self.lib.hmc_get_dist_hist(self.h, _p(out)))
         return out
 

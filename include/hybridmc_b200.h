@@ -215,8 +215,10 @@ int hmc_get_dist(hmc_handle h, double *dist, uint32_t *n_rows);
 /* config_int[R_total][cap] in the reference's append order (MD samples and
  * crankshaft samples interleaved, main.cc:205,234), n[R_total]. */
 int hmc_get_config_int(hmc_handle h, uint64_t *config_int, uint32_t *n);
-/* Fine histogram of every nonlocal-bond distance, pooled per transition:
- * hist[n_transitions][n_nonlocal][nbins] over [0, rmax). */
+/* Fine histograms of every nonlocal-bond distance, pooled per transition and split by
+ * the state of the first transient bond (index 1: its distance < rc, else 0) — the
+ * sufficient statistics of tools/mfpt.py (the on/off split of mfpt.py:104-125):
+ * hist[n_transitions][n_nonlocal][2][nbins] over [0, rmax), one count per MD step. */
 int hmc_enable_dist_hist(hmc_handle h, unsigned nbins, double rmax);
 int hmc_get_dist_hist(hmc_handle h, uint64_t *hist);
 /* First recorded configuration with config == 1 per replica
