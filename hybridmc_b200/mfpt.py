@@ -1,0 +1,129 @@
+"""First-passage times from bond-distance statistics — a self-contained restatement of
+the reference's `tools/mfpt.py:153-381` (which needs nlopt, h5py and
+`scipy.integrate.quadrature`, none of which exist in this image; versions unpinned in
+the reference, so this boundary is "parity unpinned" and validated statistically against
+the published `crambin_s_bias_mfpt/mfpt.csv`).
+
+Model (mfpt.py:372-381, 211-222, 340-369): the potential of mean force -ln p(r) on
+[lo, hi] is a NATURAL cubic spline through `nknots` = 14 equally spaced knots whose
+ordinates maximise the likelihood of the sampled distances,
+        f(y) = mean_i S(r_i; y) + ln Integral_lo^hi exp(-S(r; y)) dr,
+and with pdf = exp(-S)/Z, cdf its integral,
+        inner fpt = Integral cdf^2 / pdf dr        (bond formed, r in [rh, rc])
+        outer fpt = Integral (1 - cdf)^2 / pdf dr  (bond open, r in [rc, r_max]).
+Because S is linear in the knot ordinates (cardinal natural splines), f is convex; it is
+minimised here with scipy's L-BFGS (the reference: nlopt LD_LBFGS, rel. tol 5e-5) using
+Gauss-Legendre quadrature per knot interval.  Works on raw samples (the `dist` dataset)
+or on the engine's pooled histograms (`hmc_get_dist_hist`), i.e. a binned likelihood.
+"""
+import numpy as np
+from scipy import interpolate, optimize
+
+NKNOTS = 14  # mfpt.py:62
+
+
+def _basis(x_knot, x):
+    """B[i, k] = value at x[i] of the natural cubic spline that is 1 at knot k, 0 at the
+    others (scipy CubicSpline(bc_type='natural'), as mfpt.py:172)."""
+    eye = np.eye(len(x_knot))
+    spl = interpolate.CubicSpline(x_knot, eye, bc_type="natural", axis=0)
+    return spl(np.clip(x, x_knot[0], x_knot[-1]))
+
+
+def _quadrature(x_knot, order=24):
+    """Gauss-Legendre nodes / weights on every knot interval"""
+    t, w = np.polynomial.legendre.leggauss(order)
+    a, b = x_knot[:-1, None], x_knot[1:, None]
+    nodes = 0.5 * (b - a) * t[None, :] + 0.5 * (b + a)
+    weights = 0.5 * (b - a) * w[None, :]
+    return nodes.ravel(), weights.ravel()
+
+
+def fit_pmf(x, weights, lo, hi, nknots=NKNOTS):
+    """Maximum-likelihood knot ordinates y of -ln p(r) on [lo, hi] for data points x
+    with weights (sample: weights = 1; histogram: bin centres and counts).
+    Returns (x_knot, y)."""
+    x_knot = np.linspace(lo, hi, nknots)
+    w = np.asarray(weights, dtype=float)
+    w = w / w.sum()
+    bw = _basis(x_knot, np.asarray(x, dtype=float)).T @ w  # mean_i B_k(r_i)
+    qx, qw = _quadrature(x_knot)
+    bq = _basis(x_knot, qx)
+
+    def f_df(y):
+        s = bq @ y
+        m = (-s).max()
+        e = qw * np.exp(-s - m)
+        z = e.sum()
+        return bw @ y + np.log(z) + m, bw - (bq.T @ e) / z
+
+    res = optimize.minimize(f_df, np.zeros(nknots), jac=True, method="L-BFGS-B",
+                            options=dict(maxiter=2000, ftol=1e-13, gtol=1e-9))
+    return x_knot, res.x
+
+
+def fpt_from_fit(x_knot, y, inner, order=24):
+    """mfpt.py:340-369 with pdf/cdf from the fitted spline."""
+    qx, qw = _quadrature(x_knot, order)
+    s = _basis(x_knot, qx) @ y
+    e = np.exp(-(s - s.min()))
+    z = (qw * e).sum()
+    pdf = e / z
+    # cdf at the quadrature nodes: full intervals to the left + partial interval by a
+    # second Gauss-Legendre rule on [knot, node]
+    n_int = len(x_knot) - 1
+    per = pdf.reshape(n_int, order) * qw.reshape(n_int, order)
+    left = np.concatenate([[0.0], np.cumsum(per.sum(axis=1))[:-1]])
+    t, w = np.polynomial.legendre.leggauss(order)
+    cdf = np.empty_like(pdf)
+    for i in range(n_int):
+        a = x_knot[i]
+        for j in range(order):
+            b = qx[i * order + j]
+            xx = 0.5 * (b - a) * t + 0.5 * (b + a)
+            ss = _basis(x_knot, xx) @ y
+            cdf[i * order + j] = left[i] + (0.5 * (b - a) * w * np.exp(-(ss - s.min())) / z).sum()
+    integrand = cdf * cdf / pdf if inner else (1.0 - cdf) * (1.0 - cdf) / pdf
+    return float((qw * integrand).sum())
+
+
+def fpt_from_samples(dist, lo, hi, inner, nknots=NKNOTS):
+    """fpt_per_bead_pair, mfpt.py:372-381, on raw samples restricted to [lo, hi]."""
+    d = np.asarray(dist, dtype=float)
+    d = d[(d >= lo) & (d <= hi)]
+    if len(d) < nknots:
+        raise ValueError("too few samples in [%g, %g]" % (lo, hi))
+    xk, y = fit_pmf(d, np.ones(len(d)), lo, hi, nknots)
+    return fpt_from_fit(xk, y, inner)
+
+
+def fpt_from_hist(counts, rmax, lo, hi, inner, nknots=NKNOTS):
+    """The same from a histogram of `len(counts)` equal bins over [0, rmax) (binned
+    likelihood: every sample sits at its bin centre).  Bins are clipped to [lo, hi]; for
+    the outer time hi=None means "up to the last occupied bin" (mfpt.py:137: max(t_off))."""
+    counts = np.asarray(counts, dtype=float)
+    n = len(counts)
+    width = rmax / n
+    centres = (np.arange(n) + 0.5) * width
+    if hi is None:
+        nz = np.nonzero(counts)[0]
+        hi = (nz[-1] + 1) * width
+    sel = (centres >= lo) & (centres <= hi) & (counts > 0)
+    if sel.sum() < 4:
+        raise ValueError("too few occupied bins in [%g, %g]" % (lo, hi))
+    xk, y = fit_pmf(centres[sel], counts[sel], lo, hi, nknots)
+    return fpt_from_fit(xk, y, inner)
+
+
+def transition_fpts(hist, rmax, params, bond_column=None):
+    """(inner fpt, outer fpt) of a transition's transient bond from the engine's histograms
+    hist[n_nonlocal][2][nbins] (index 1 = transient bond formed): the two numbers a row of
+    the reference's mfpt.csv holds."""
+    if bond_column is None:
+        t = params.bond_list("transient")[0]
+        cols = sorted(params.bond_list("nonlocal"))  # dist columns are in (i,j) scan order
+        bond_column = cols.index(t)
+    h = np.asarray(hist)[bond_column]
+    inner = fpt_from_hist(h[1], rmax, params.rh, params.rc, True)
+    outer = fpt_from_hist(h[0], rmax, params.rc, None, False)
+    return inner, outer

@@ -15,6 +15,7 @@ sys.path.insert(0, ROOT)
 from bench import load_master  # noqa: E402
 from hybridmc_b200.campaign import layers_of, run_transition_ensemble  # noqa: E402
 from hybridmc_b200.engine import init_pos_chain  # noqa: E402
+from hybridmc_b200 import mfpt  # noqa: E402
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 8
@@ -32,7 +33,8 @@ t0 = time.time()
 runs = []
 for seed in range(nseeds):
     out = run_transition_ensemble(params, [pos0] * len(trans), R, seed=(900 + seed, 5),
-                                  iters_per_round=iters, eq_iters=8, max_rounds=rounds)
+                                  iters_per_round=iters, eq_iters=8, max_rounds=rounds,
+                                  hist_bins=16384, hist_rmax=master["length"] * 0.5 * 3 ** 0.5)
     runs.append(out)
     print("run", seed, "rounds", out["rounds"].tolist(), "accepted", out["accepted"].tolist(),
           "err", int(np.bitwise_or.reduce(out["err"])), "events", out["events"].tolist(),
@@ -48,3 +50,17 @@ for k, (bits_in, bits_out, p) in enumerate(trans):
     print("%-12s %-10s %10.4f %10.4f %10.4f %8.4f" % (fmt(bits_out), p.bond_list("transient")[0],
                                                        mean, half, ref, mean - ref))
 print("largest |gpu - published| = %.4f" % worst)
+
+print()
+print("%-12s %-10s %12s %12s %12s %12s" % ("bits_out", "bond", "inner_gpu", "inner_pub", "outer_gpu", "outer_pub"))
+rmax = master["length"] * 0.5 * 3 ** 0.5
+for k, (bits_in, bits_out, p) in enumerate(trans):
+    hist = sum(r["dist_hist"][k].astype(np.float64) for r in runs)
+    try:
+        inner, outer = mfpt.transition_fpts(hist, rmax, p)
+    except Exception as exc:
+        inner = outer = float("nan")
+        print("fit failed:", exc)
+    ref = pub["mfpt_layer0"][fmt(bits_out)]
+    print("%-12s %-10s %12.5f %12.5f %12.3f %12.3f" % (fmt(bits_out), p.bond_list("transient")[0],
+                                                       inner, ref["inner"], outer, ref["outer"]))

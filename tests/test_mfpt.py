@@ -1,0 +1,61 @@
+"""CPU: the restated first-passage-time estimator (hybridmc_b200/mfpt.py, after
+tools/mfpt.py) on distributions with known answers, and samples vs histogram input."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import load_config
+from hybridmc_b200 import mfpt
+from hybridmc_b200.params import params_from_json
+
+
+def test_uniform_density_has_analytic_fpt():
+    # p = 1/(b-a): inner = Int ((x-a)/(b-a))^2 (b-a) dx = (b-a)^2 / 3, outer the same
+    rng = np.random.default_rng(0)
+    a, b = 1.25, 1.5
+    x = rng.uniform(a, b, 200000)
+    assert abs(mfpt.fpt_from_samples(x, a, b, True) / ((b - a) ** 2 / 3) - 1) < 0.02
+    assert abs(mfpt.fpt_from_samples(x, a, b, False) / ((b - a) ** 2 / 3) - 1) < 0.02
+
+
+def test_r2_density_matches_numeric_integral():
+    # p(r) ~ r^2 on [1.5, 9] (free relative diffusion in 3-D)
+    rng = np.random.default_rng(1)
+    lo, hi = 1.5, 9.0
+    u = rng.uniform(0, 1, 400000)
+    x = (lo ** 3 + u * (hi ** 3 - lo ** 3)) ** (1 / 3)
+    r = np.linspace(lo, hi, 200001)
+    pdf = 3 * r ** 2 / (hi ** 3 - lo ** 3)
+    cdf = (r ** 3 - lo ** 3) / (hi ** 3 - lo ** 3)
+    exact = np.trapezoid((1 - cdf) ** 2 / pdf, r)
+    est = mfpt.fpt_from_samples(x, lo, hi, False)
+    assert abs(est / exact - 1) < 0.03
+    counts, edges = np.histogram(x, bins=4096, range=(0, 16.0))
+    est_h = mfpt.fpt_from_hist(counts, 16.0, lo, hi, False)
+    assert abs(est_h / est - 1) < 0.01
+
+
+def test_samples_and_histogram_agree_on_simulated_distances(oracle):
+    """dist rows of a short reference-exact 8bead_1bond program (oracle)"""
+    from oracle_lib import OrcMainResult
+    p = params_from_json(load_config("8bead_1bond", total_iter=150, total_iter_eq=20))
+    r = OrcMainResult()
+    cap = 150 * 8 * 3
+    d = np.zeros((cap, 1))
+    n = C.c_uint(0)
+    assert oracle.orc_run_main(C.byref(p), None, 3, cap, d.ctypes.data_as(C.c_void_p), C.byref(n),
+                               C.byref(r)) == 0
+    x = d[:n.value, 0]
+    on, off = x[x < p.rc], x[x >= p.rc]
+    if len(on) < 200 or len(off) < 200:
+        pytest.skip("too few samples on one side")
+    rmax = 18.0 * 0.5 * 3 ** 0.5
+    inner_s = mfpt.fpt_from_samples(on, p.rh, p.rc, True)
+    outer_s = mfpt.fpt_from_samples(off, p.rc, off.max(), False)
+    h_on, _ = np.histogram(on, bins=16384, range=(0, rmax))
+    h_off, _ = np.histogram(off, bins=16384, range=(0, rmax))
+    inner_h = mfpt.fpt_from_hist(h_on, rmax, p.rh, p.rc, True)
+    outer_h = mfpt.fpt_from_hist(h_off, rmax, p.rc, None, False)
+    assert abs(inner_h / inner_s - 1) < 0.05 and abs(outer_h / outer_s - 1) < 0.05
+    assert 0.005 < inner_s < 0.05 and 0.5 < outer_s < 50  # same order as mfpt.csv short loops
