@@ -104,6 +104,16 @@ struct Rep {
   bool live; // false: a clone filling an idle group of the warp; no global side effects
 };
 
+// "does any replica group of this warp satisfy p" for a GROUP-UNIFORM predicate: with one
+// group per warp (G == 32) that is p itself and no vote instruction is needed.
+template <int G> __device__ __forceinline__ bool warp_any(bool p) {
+  if constexpr (G == 32) {
+    return p;
+  } else {
+    return __any_sync(0xffffffffu, p);
+  }
+}
+
 template <int G> __device__ __forceinline__ unsigned group_mask() {
   if constexpr (G == 32) {
     return 0xffffffffu;
@@ -483,15 +493,17 @@ __device__ __forceinline__ unsigned check_constraints(const KArgs &a, const Rep 
 // initialize_system, main.cc:45-95: constraint checks, init_cells, velocities
 // (+ COM shift), and the full prediction fill of the event table.
 template <int G>
+// Executed by the whole warp; only groups with `on` change their state (the others are in
+// the middle of a step).
 __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *normals,
-                          unsigned long long draw, int lane, unsigned gmask) {
+                          unsigned long long draw, int lane, unsigned gmask, bool on) {
   const int nb = a.nb;
   const unsigned ok = check_constraints<G>(a, R, s.b + F_X, false, lane, gmask);
-  if (!(ok & 1u)) R.err |= HMC_ERR_LOCAL_OVERLAP;
-  if (!(ok & 2u)) R.err |= HMC_ERR_NONLOCAL_OVERLAP;
+  if (on && !(ok & 1u)) R.err |= HMC_ERR_LOCAL_OVERLAP;
+  if (on && !(ok & 2u)) R.err |= HMC_ERR_NONLOCAL_OVERLAP;
 
   // init_cells (hardspheres.cc:334-369) + raw velocity draws (init_vel :197-209)
-  for (int k = lane; k < nb; k += G) {
+  for (int k = lane; k < nb && on; k += G) {
     double x = BX(s, k), y = BY(s, k), z = BZ(s, k);
     x -= floor(x * a.inv_l) * a.l; // Box::minpos
     y -= floor(y * a.inv_l) * a.l;
@@ -540,7 +552,7 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
   }
   const double cmx = tx / double(nb), cmy = ty / double(nb), cmz = tz / double(nb);
   __syncwarp();
-  for (int k = lane; k < nb; k += G) {
+  for (int k = lane; k < nb && on; k += G) {
     BVX(s, k) -= cmx;
     BVY(s, k) -= cmy;
     BVZ(s, k) -= cmz;
@@ -548,7 +560,7 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
   __syncwarp();
 
   // init_cell_events (hardspheres.cc:696-704)
-  for (int k = lane; k < nb; k += G) {
+  for (int k = lane; k < nb && on; k += G) {
     const Bead b = load_bead(s, k);
     double t;
     unsigned wall = 0;
@@ -568,8 +580,8 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
       doit = mine && (adj_mask(BCELL(s, i), BCELL(s, j), unsigned(a.ncell - 1) * 0x00010101u) &
                       0x00ffffffu) == 0x00ffffffu;
     double tt;
-    const unsigned ty = predict_pair(a, R, s, i, j, true, d, __ldg(&R.pinfo[p]), doit, tt);
-    if (mine) {
+    const unsigned ty = predict_pair(a, R, s, i, j, true, d, __ldg(&R.pinfo[p]), doit && on, tt);
+    if (mine && on) {
       s.evt[nb + p] = (ty != 0xffu) ? tt : CUDART_INF;
       s.evty[nb + p] = uint8_t(ty);
     }
@@ -579,46 +591,40 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
 
 // --------------------------------------------------------- the event loop --
 
-// run_step, main.cc:97-149: process every event with t <= step_time, then advance
-// all beads to step_time.
+// Lane-strided argmin over the event table of the group + shuffle reduce
+// (ties -> lowest slot).  Replaces EventQueue::top() (event.h:105-116).
+template <int G>
+__device__ __forceinline__ void table_argmin(const Smem &s, int nslots, int lane, double &bt,
+                                             int &bs) {
+  bt = CUDART_INF;
+  bs = 0x7fffffff;
+  for (int q = lane; q < nslots; q += G) {
+    const double t = s.evt[q];
+    const bool lt = t < bt;
+    bt = lt ? t : bt;
+    bs = lt ? q : bs;
+  }
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) {
+    const double ot = __shfl_xor_sync(0xffffffffu, bt, off);
+    const int os = __shfl_xor_sync(0xffffffffu, bs, off);
+    const bool take = ot < bt || (ot == bt && os < bs);
+    bt = take ? ot : bt;
+    bs = take ? os : bs;
+  }
+}
+
+// One event of run_step's loop (main.cc:107-132) for every group of the warp that has
+// one (`has`); the others are predicated off.
 //
 // The body is one instruction path for collisions and cell crossings alike (selects
-// instead of branches): the replica groups that share a warp execute it in lockstep,
-// and a crossing simply discards the collision arithmetic it did not need.
+// instead of branches): the replica groups that share a warp execute it together, and
+// a crossing simply discards the collision arithmetic it did not need.
 template <int G>
-__device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_time, int lane,
-                           unsigned gmask) {
-  const int nb = a.nb, nslots = a.nslots, nc = a.ncell;
-  unsigned guard = 0;
-  bool overrun = false;
-  for (;;) {
-    // a step of the shipped configurations has 5e2-1e4 events; a runaway replica
-    // (non-finite state) is flagged and abandoned instead of hanging the device
-    if (++guard > a.max_events_per_step) {
-      R.err |= HMC_ERR_NAN;
-      overrun = true;
-    }
-    // ---- argmin over the event table (ties -> lowest slot) ----
-    double bt = CUDART_INF;
-    int bs = 0x7fffffff;
-    for (int q = lane; q < nslots; q += G) {
-      const double t = s.evt[q];
-      const bool lt = t < bt;
-      bt = lt ? t : bt;
-      bs = lt ? q : bs;
-    }
-#pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1) {
-      const double ot = __shfl_xor_sync(0xffffffffu, bt, off);
-      const int os = __shfl_xor_sync(0xffffffffu, bs, off);
-      const bool take = ot < bt || (ot == bt && os < bs);
-      bt = take ? ot : bt;
-      bs = take ? os : bs;
-    }
-    // groups whose step is finished idle (predicated off) until every group of the
-    // warp is done
-    const bool has = (bt <= step_time) && !overrun;
-    if (!__any_sync(0xffffffffu, has)) break;
+__device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s, bool has,
+                                           double bt, int bs, int lane) {
+  const int nb = a.nb, nc = a.ncell;
+  {
     bs = has ? bs : 0;
 
     const double t = bt;
@@ -789,7 +795,7 @@ __device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_ti
       const unsigned others = 0x00ffffffu & ~(0xffu << (8 * axis)); // the two other axes
       const int nitem = nbead * nb;
       // warp-uniform trip count: 2*nb unless every group of the warp has a crossing
-      const int nloop = __any_sync(0xffffffffu, has && !is_cell) ? 2 * nb : nb;
+      const int nloop = warp_any<G>(has && !is_cell) ? 2 * nb : nb;
       for (int base = 0; base < nloop; base += G) {
         const int idx = base + lane;
         const bool second = idx >= nb;
@@ -823,8 +829,13 @@ __device__ void run_events(const KArgs &a, Rep &R, const Smem &s, double step_ti
       __syncwarp();
     }
   }
-  // advance every bead to step_time (main.cc:135-138)
-  for (int k = lane; k < nb; k += G) {
+}
+
+// end of run_step: advance every bead to step_time (main.cc:135-138)
+template <int G>
+__device__ __forceinline__ void advance_all(const KArgs &a, const Smem &s, double step_time,
+                                            int lane, bool on) {
+  for (int k = lane; k < a.nb && on; k += G) {
     const double dt = step_time - BT(s, k);
     BX(s, k) += BVX(s, k) * dt;
     BY(s, k) += BVY(s, k) * dt;
@@ -844,61 +855,64 @@ __device__ __forceinline__ void record_config_int(const KArgs &a, const Rep &R, 
   }
 }
 
-// body of run_trajectory after run_step, main.cc:199-225
+// body of run_trajectory after run_step, main.cc:199-225 (whole warp executes; only
+// groups with `on` sample; `step` may differ between the groups of a warp)
 template <int G>
 __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step, double e0,
-                            int lane, unsigned gmask) {
+                            int lane, bool on) {
   const int trans = R.r / a.replicas_per_trans;
+  const bool out = on && R.live; // global side effects
   // dist_between_nonlocal_beads (hardspheres.cc:1084-1104)
   if (a.dist_cap || a.hist_bins) {
-    const unsigned nrow = a.dist_cap ? a.dist_n[R.r] : 0u;
+    const unsigned nrow = (a.dist_cap && out) ? a.dist_n[R.r] : 0u;
     // the histograms are split by the state of the first transient bond, r_t < rc, the
     // split tools/mfpt.py applies to the dist rows (mfpt.py:104-125)
-    int on = 0;
+    int st_on = 0;
     if (a.hist_bins && R.tr->n_transient)
-      on = dist2_ij(a, s.b + F_X, R.tr->tb_i[0], R.tr->tb_j[0]) < R.rc2 ? 1 : 0;
-    for (int k = lane; k < int(R.tr->n_nonlocal); k += G) {
+      st_on = dist2_ij(a, s.b + F_X, R.tr->tb_i[0], R.tr->tb_j[0]) < R.rc2 ? 1 : 0;
+    for (int k = lane; k < int(R.tr->n_nonlocal) && out; k += G) {
       const int i = R.tr->nl_i[k], j = R.tr->nl_j[k];
       const double d = sqrt(dist2_ij(a, s.b + F_X, i, j));
-      if (a.dist_cap && nrow < a.dist_cap && R.live)
+      if (a.dist_cap && nrow < a.dist_cap)
         a.dist[(size_t(R.r) * a.dist_cap + nrow) * a.dist_stride + k] = d;
-      if (a.hist_bins && R.live) {
+      if (a.hist_bins) {
         int bin = int(d * a.hist_scale);
         bin = min(max(bin, 0), int(a.hist_bins) - 1);
-        atomicAdd(&a.hist[((size_t(trans) * a.dist_stride + k) * 2 + on) * a.hist_bins + bin], 1ull);
+        atomicAdd(&a.hist[((size_t(trans) * a.dist_stride + k) * 2 + st_on) * a.hist_bins + bin], 1ull);
       }
     }
     __syncwarp();
-    if (a.dist_cap && lane == 0 && R.live) {
+    if (a.dist_cap && lane == 0 && out) {
       if (nrow >= a.dist_cap) R.err |= HMC_ERR_SAMPLE_OVERFLOW;
       a.dist_n[R.r] = nrow + 1;
     }
   }
-  if (step % a.write_step == 0) {
+  const bool rec = on && (step % a.write_step == 0);
+  if (rec) {
     if (lane == 0 && R.live && R.config < (unsigned long long)a.nstates)
       atomicAdd(&a.acc[size_t(trans) * a.nstates + R.config], 1ull);
     record_config_int(a, R, lane);
-    // unique_config: first recorded sample with config == 1 (main.cc:211-216)
-    const bool take = R.live && R.config == 1ull && !a.uniq_found[R.r];
-    __syncwarp();
-    if (take) {
-      for (int k = lane; k < a.nb; k += G) {
-        double *up = a.uniq_pos + (size_t(R.r) * a.nb + k) * 3;
-        double *uv = a.uniq_vel + (size_t(R.r) * a.nb + k) * 3;
-        up[0] = BX(s, k);
-        up[1] = BY(s, k);
-        up[2] = BZ(s, k);
-        uv[0] = BVX(s, k);
-        uv[1] = BVY(s, k);
-        uv[2] = BVZ(s, k);
-      }
-      if (lane == 0) a.uniq_found[R.r] = 1;
-    }
-    __syncwarp();
   }
+  // unique_config: first recorded sample with config == 1 (main.cc:211-216)
+  const bool take = rec && R.live && R.config == 1ull && !a.uniq_found[R.r];
+  __syncwarp();
+  if (take) {
+    for (int k = lane; k < a.nb; k += G) {
+      double *up = a.uniq_pos + (size_t(R.r) * a.nb + k) * 3;
+      double *uv = a.uniq_vel + (size_t(R.r) * a.nb + k) * 3;
+      up[0] = BX(s, k);
+      up[1] = BY(s, k);
+      up[2] = BZ(s, k);
+      uv[0] = BVX(s, k);
+      uv[1] = BVY(s, k);
+      uv[2] = BVZ(s, k);
+    }
+    if (lane == 0) a.uniq_found[R.r] = 1;
+  }
+  __syncwarp();
   const double e1 = hamiltonian(a, R, s);
   const double ediff = fabs(1 - (e1 / e0));
-  if (!(ediff < 1e-6)) R.err |= HMC_ERR_ENERGY;
+  if (on && !(ediff < 1e-6)) R.err |= HMC_ERR_ENERGY;
 }
 
 // ------------------------------------------------------------- crankshaft --
@@ -909,9 +923,12 @@ __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step
 // start of every MD step; they are saved to global memory before the first move).
 template <int G>
 __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &ws,
-                            unsigned move_offset, unsigned n_moves, int lane, unsigned gmask) {
+                            unsigned move_offset, unsigned n_moves, int lane, unsigned gmask,
+                            bool on) {
   const int nb = a.nb;
-  bool dead = false; // tape ran out: this group sits out the remaining moves
+  // dead: this group sits the moves out (it is not at a crankshaft point of its
+  // schedule, or its tape ran out)
+  bool dead = !on;
   for (unsigned mv = 0; mv < n_moves; mv++) {
     const unsigned start = ws.c;
     unsigned attempts = 0;
@@ -920,7 +937,7 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
     // valid trial are predicated off until every group of the warp has one
     for (;;) {
       const bool need = !ok && !dead;
-      if (!__any_sync(0xffffffffu, need)) break;
+      if (!warp_any<G>(need)) break;
       unsigned ind = 1;
       double sn = 0.0, cs = 1.0;
       bool drew = false;
@@ -1120,8 +1137,8 @@ template <int G> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hm
     ws.buf_blk = 0xffffffffu;
 
     bool vel_dirty = false; // velocity arrays hold crankshaft scratch
-    auto save_vel = [&]() {
-      if (live) {
+    auto save_vel = [&](bool on) {
+      if (live && on) {
         for (int k = lane; k < nb; k += G) {
           double *v = a.vel + (size_t(r) * nb + k) * 3;
           v[0] = BVX(s, k);
@@ -1133,77 +1150,118 @@ template <int G> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hm
     };
 
     if (a.op == HMC_OP_CRANK_ONLY) {
-      crank_moves<G>(a, R, s, ws, a.move_offset, a.count, lane, gmask);
+      crank_moves<G>(a, R, s, ws, a.move_offset, a.count, lane, gmask, true);
       vel_dirty = true;
       if (lane == 0 && live && a.tape_consumed) {
         a.tape_consumed[r] = ws.c;
         a.tape_consumed[a.n_replicas + r] = R.moves_done;
       }
     } else {
-      unsigned long long draw = a.md_draw_base; // one draw index per initialize_system
-      unsigned inj = 0;                          // injected-normals row
-      auto normals_row = [&]() -> const double * {
-        return a.normals ? a.normals + (size_t(r) * a.count + inj) * size_t(nb) * 3 : nullptr;
-      };
-      for (unsigned it = 0; it < a.count; it++) {
-        if (a.phase == HMC_PHASE_WL) {
-          // wang_landau / run_trajectory_wl, main.cc:249-305
-          // RUN: `it` = outer iteration offset (nstates trajectories each);
-          // MD_ONLY: `it` = trajectory offset
-          const unsigned ntraj = (a.op == HMC_OP_RUN) ? unsigned(a.nstates) : 1u;
-          for (unsigned q = 0; q < ntraj; q++) {
-            const unsigned iter_wl =
-                (a.op == HMC_OP_RUN) ? a.first + it : (a.first + it) / unsigned(a.nstates);
-            init_step<G>(a, R, s, normals_row(), draw, lane, gmask);
-            draw++;
-            inj++;
-            const double e0 = hamiltonian(a, R, s);
-            for (unsigned st = iter_wl * a.nsteps_wl; st < (iter_wl + 1) * a.nsteps_wl; st++) {
-              run_events<G>(a, R, s, double(st) * a.del_t_wl, lane, gmask);
-              const double e1 = hamiltonian(a, R, s);
-              if (!(fabs(1 - (e1 / e0)) < 1e-6)) R.err |= HMC_ERR_ENERGY;
+      // ---- the replica's schedule as a flat list of event steps e = 0 .. E-1 ----
+      //   EQ / MAIN : one initialize_system per step (main.cc:154-163, 185-197)
+      //   WL        : one initialize_system per trajectory of nsteps_wl steps
+      //               (run_trajectory_wl, main.cc:249-276), then the +-gamma update
+      // The groups of a warp walk this list independently: a group whose step has no
+      // event left does its step-end / next-step work while the others keep processing
+      // events (all of it executed warp-wide under predicates), so nobody waits for the
+      // slowest replica of the warp at every step.
+      const bool wl = a.phase == HMC_PHASE_WL;
+      const unsigned per = wl ? a.nsteps_wl : (a.op == HMC_OP_RUN ? (a.phase == HMC_PHASE_EQ ? a.nsteps_eq : a.nsteps) : 1u);
+      const unsigned nunits = wl && a.op == HMC_OP_RUN ? a.count * unsigned(a.nstates) : a.count;
+      const unsigned E = nunits * per; // units: iterations (RUN), trajectories (WL), steps (MD_ONLY)
+      unsigned e = 0;                  // next / current event step of this group
+      unsigned ninit = 0;              // initialize_system calls so far (RNG draw index)
+      bool in_step = false;
+      double step_time = 0.0, e0 = 0.0;
+      unsigned cur_st = 0;
+      unsigned guard = 0;
+      for (;;) {
+        // -- start the next step --
+        const bool start = !in_step && e < E;
+        if (warp_any<G>(start)) {
+          const unsigned unit = e / per, sub = e - unit * per;
+          unsigned st;
+          if (wl) {
+            const unsigned iter_wl = a.op == HMC_OP_RUN ? a.first + unit / unsigned(a.nstates)
+                                                        : (a.first + unit) / unsigned(a.nstates);
+            st = iter_wl * a.nsteps_wl + sub;
+          } else {
+            st = a.op == HMC_OP_RUN ? (a.first + unit) * per + sub : a.first + unit;
+          }
+          const bool do_init = start && (!wl || sub == 0);
+          if (warp_any<G>(do_init)) {
+            const double *nrm =
+                (a.normals && do_init) ? a.normals + (size_t(r) * nunits + ninit) * size_t(nb) * 3
+                                       : nullptr;
+            init_step<G>(a, R, s, nrm, a.md_draw_base + ninit, lane, gmask, do_init);
+            const double h0 = hamiltonian(a, R, s);
+            if (do_init) {
+              e0 = h0;
+              ninit++;
             }
-            const double g = wl_gamma(a, iter_wl);
-            __syncwarp();
-            if (lane == 0 && live) {
+          }
+          if (start) {
+            cur_st = st;
+            step_time = double(st) * (wl ? a.del_t_wl : a.del_t);
+            in_step = true;
+            guard = 0;
+          }
+        }
+        // -- next event of the current step --
+        double bt;
+        int bs;
+        table_argmin<G>(s, a.nslots, lane, bt, bs);
+        // a step of the shipped configurations has 5e2-1e4 events; a runaway replica
+        // (non-finite state) is flagged and its step cut short instead of hanging
+        const bool overrun = in_step && ++guard > a.max_events_per_step;
+        if (overrun) R.err |= HMC_ERR_NAN;
+        const bool has = in_step && (bt <= step_time) && !overrun;
+        // -- finish the step --
+        const bool finish = in_step && !has;
+        if (warp_any<G>(finish)) {
+          advance_all<G>(a, s, step_time, lane, finish);
+          const unsigned unit = e / per, sub = e - unit * per;
+          if (a.phase == HMC_PHASE_MAIN) {
+            sample_step<G>(a, R, s, cur_st, e0, lane, finish);
+          } else if (wl) {
+            const double e1 = hamiltonian(a, R, s);
+            if (finish && !(fabs(1 - (e1 / e0)) < 1e-6)) R.err |= HMC_ERR_ENERGY;
+            // wang_landau, main.cc:288-304
+            if (finish && sub + 1 == per && lane == 0 && live) {
+              const unsigned iter_wl = a.op == HMC_OP_RUN ? a.first + unit / unsigned(a.nstates)
+                                                          : (a.first + unit) / unsigned(a.nstates);
+              const double g = wl_gamma(a, iter_wl);
               if (R.config == 0ull) R.sb[a.nstates - 1] -= g;
               else R.sb[a.nstates - 1] += g;
             }
             __syncwarp();
           }
-        } else {
-          const unsigned nsteps = (a.phase == HMC_PHASE_EQ) ? a.nsteps_eq : a.nsteps;
-          unsigned st0, st1;
-          if (a.op == HMC_OP_RUN) {
-            st0 = (a.first + it) * nsteps;
-            st1 = st0 + nsteps;
-          } else {
-            st0 = a.first + it;
-            st1 = st0 + 1;
-          }
-          for (unsigned st = st0; st < st1; st++) {
-            init_step<G>(a, R, s, normals_row(), draw, lane, gmask);
-            draw++;
-            inj++;
-            if (a.phase == HMC_PHASE_EQ) {
-              run_events<G>(a, R, s, double(st) * a.del_t, lane, gmask);
-            } else {
-              const double e0 = hamiltonian(a, R, s);
-              run_events<G>(a, R, s, double(st) * a.del_t, lane, gmask);
-              sample_step<G>(a, R, s, st, e0, lane, gmask);
+          // crankshaft block after the last MD step of an iteration (main.cc:228-237)
+          const bool crank = finish && a.op == HMC_OP_RUN && a.phase == HMC_PHASE_MAIN &&
+                             a.mc_moves != 0 && sub + 1 == per;
+          if (warp_any<G>(crank)) {
+            save_vel(crank);
+            if (crank) {
+              const unsigned long long mcd = a.mc_draw_base + unit;
+              ws.c = 0;
+              ws.c1 = unsigned(mcd);
+              ws.c2 = unsigned(mcd >> 32) | 0x80000000u;
+              ws.buf_blk = 0xffffffffu;
+              vel_dirty = true;
             }
+            crank_moves<G>(a, R, s, ws, 0u, a.mc_moves, lane, gmask, crank);
           }
-          if (a.op == HMC_OP_RUN && a.phase == HMC_PHASE_MAIN && a.mc_moves) {
-            save_vel();
-            const unsigned long long mcd = a.mc_draw_base + it;
-            ws.c = 0;
-            ws.c1 = unsigned(mcd);
-            ws.c2 = unsigned(mcd >> 32) | 0x80000000u;
-            ws.buf_blk = 0xffffffffu;
-            crank_moves<G>(a, R, s, ws, 0u, a.mc_moves, lane, gmask);
-            vel_dirty = true;
+          if (finish) {
+            in_step = false;
+            e++;
+            vel_dirty = crank; // a later init_step redraws the velocities
           }
         }
+        if (!warp_any<G>(has)) {
+          if (!warp_any<G>(in_step || e < E)) break;
+          continue;
+        }
+        event_body<G>(a, R, s, has, bt, bs, lane);
       }
     }
 
@@ -1217,7 +1275,7 @@ template <int G> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hm
         p[2] = BZ(s, k);
       }
     }
-    if (!vel_dirty) save_vel();
+    save_vel(!vel_dirty);
     if (lane == 0 && live) {
       a.config[r] = R.config;
       if (R.err) atomicOr(&a.err[r], R.err);

@@ -21,7 +21,8 @@ R = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 nseeds = int(sys.argv[4]) if len(sys.argv) > 4 else 2
-select = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else None
+select = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 and sys.argv[5] != "all" else None
+eq_iters = int(sys.argv[6]) if len(sys.argv) > 6 else 8
 pub = json.load(open(os.path.join(ROOT, "tests", "golden", "crambin_published_s_bias_subset.json")))
 master = load_master("crambin")
 trans = layers_of(master)[0][1]
@@ -33,7 +34,7 @@ t0 = time.time()
 runs = []
 for seed in range(nseeds):
     out = run_transition_ensemble(params, [pos0] * len(trans), R, seed=(900 + seed, 5),
-                                  iters_per_round=iters, eq_iters=8, max_rounds=rounds,
+                                  iters_per_round=iters, eq_iters=eq_iters, max_rounds=rounds,
                                   hist_bins=16384, hist_rmax=master["length"] * 0.5 * 3 ** 0.5)
     runs.append(out)
     print("run", seed, "rounds", out["rounds"].tolist(), "accepted", out["accepted"].tolist(),
