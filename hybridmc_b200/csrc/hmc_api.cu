@@ -882,6 +882,37 @@ int hmc_g_test(const uint64_t *cc, int n, double sig, double *g_val, double *g_c
   return (g < crit) ? 1 : 0;
 }
 
+int hmc_get_schedule_state(hmc_handle h, hmc_schedule_state *out) {
+  if (!h || !out) return fail(h, "hmc_get_schedule_state: null");
+  const int rc = sync(h);
+  out->t_now = h->t_now;
+  out->md_draws = h->md_draws;
+  out->mc_draws = h->mc_draws;
+  out->seed0 = h->seed0;
+  out->seed1 = h->seed1;
+  return rc;
+}
+
+int hmc_set_schedule_state(hmc_handle h, const hmc_schedule_state *in) {
+  if (!h || !in) return fail(h, "hmc_set_schedule_state: null");
+  const int rc = sync(h);
+  h->t_now = in->t_now;
+  h->md_draws = in->md_draws;
+  h->mc_draws = in->mc_draws;
+  h->seed0 = in->seed0;
+  h->seed1 = in->seed1;
+  return rc;
+}
+
+int hmc_set_s_bias_per_replica(hmc_handle h, const double *s_bias, int nstates) {
+  if (!h || !s_bias) return fail(h, "hmc_set_s_bias_per_replica: null");
+  if (nstates != h->nstates) return fail(h, "hmc_set_s_bias_per_replica: nstates mismatch");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_sbias, s_bias, sizeof(double) * size_t(h->R) * nstates,
+                     cudaMemcpyHostToDevice, h->stream));
+  return sync(h);
+}
+
 int hmc_get_launch_stats(hmc_handle h, uint64_t *n_launches, float *last_ms) {
   if (!h) return fail(h, "null handle");
   int rc = sync(h);

@@ -35,7 +35,8 @@ EXPORTS = [
     "hmc_get_unique_config", "hmc_enable_trace", "hmc_get_trace", "hmc_compute_entropy",
     "hmc_compute_g_val", "hmc_g_test", "hmc_wl_outer_iterations", "hmc_get_launch_stats", "hmc_init_pos_chain", "hmc_fp64_peak",
     "hmc_get_moves_done", "hmc_init_pos_engine", "hmc_run_program_exact",
-    "hmc_run_program_exact_sink",
+    "hmc_run_program_exact_sink", "hmc_get_schedule_state", "hmc_set_schedule_state",
+    "hmc_set_s_bias_per_replica",
 ]
 
 _lib = None
@@ -43,6 +44,11 @@ _lib = None
 
 class EngineError(RuntimeError):
     pass
+
+
+class ScheduleState(C.Structure):
+    _fields_ = [("t_now", C.c_double), ("md_draws", C.c_uint64), ("mc_draws", C.c_uint64),
+                ("seed0", C.c_uint32), ("seed1", C.c_uint32)]
 
 
 def load_library(path=None):
@@ -274,6 +280,21 @@ class Engine:
         n = C.c_uint()
         self._ck(self.lib.hmc_get_trace(self.h, _p(buf), C.c_uint(self._trace_cap), C.byref(n)))
         return buf[:min(n.value, self._trace_cap)], int(n.value)
+
+    # -- snapshot / resume (ensemble form of src/snapshot.cc) --
+    def snapshot(self):
+        st = ScheduleState()
+        self._ck(self.lib.hmc_get_schedule_state(self.h, C.byref(st)))
+        return dict(pos=self.get_positions(), config=self.get_config(), s_bias=self.get_s_bias(),
+                    schedule=(st.t_now, st.md_draws, st.mc_draws, st.seed0, st.seed1))
+
+    def restore(self, snap):
+        self.set_positions(snap["pos"])
+        self.set_config(snap["config"])
+        sb = np.ascontiguousarray(snap["s_bias"], dtype=np.float64).reshape(self.R, self.nstates)
+        self._ck(self.lib.hmc_set_s_bias_per_replica(self.h, _p(sb), self.nstates))
+        st = ScheduleState(*snap["schedule"])
+        self._ck(self.lib.hmc_set_schedule_state(self.h, C.byref(st)))
 
     def launch_stats(self):
         n, ms = C.c_uint64(), C.c_float()

@@ -329,6 +329,24 @@ int hmc_run_program_exact_sink(const hmc_params *p, int device, const double *po
  * contraction for bit parity).  Roofline denominator for bench.py. */
 int hmc_fp64_peak(int device, double *fma_tflops, double *muladd_tflops);
 
+/* ---- ensemble snapshot / resume ---------------------------------------------
+ * Together with hmc_get_positions / hmc_get_config / hmc_get_s_bias this is the
+ * ensemble form of the reference's snapshot (pos, s_bias, RNG state, config;
+ * src/snapshot.cc:14-68): the schedule state below replaces the mt19937 text because
+ * the Philox streams are counter-based.  Restoring all four on a fresh handle built
+ * from the same parameters continues the run bit-identically. */
+typedef struct hmc_schedule_state {
+  double t_now;          /* bead clocks (all beads share it at a step boundary) */
+  uint64_t md_draws;     /* initialize_system calls so far (Philox draw index) */
+  uint64_t mc_draws;     /* crankshaft blocks so far */
+  uint32_t seed0, seed1; /* Philox key */
+} hmc_schedule_state;
+int hmc_get_schedule_state(hmc_handle h, hmc_schedule_state *out);
+int hmc_set_schedule_state(hmc_handle h, const hmc_schedule_state *in);
+/* s_bias[R_total][nstates], one row per replica (counterpart of hmc_get_s_bias; the
+ * per-transition broadcast of hmc_set_s_bias loses per-replica values mid-WL). */
+int hmc_set_s_bias_per_replica(hmc_handle h, const double *s_bias, int nstates);
+
 /* ---- launch statistics (for bench.py) ------------------------------------ */
 
 /* kernels launched by this handle so far, and the device time (ms, CUDA

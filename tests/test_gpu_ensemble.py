@@ -96,3 +96,26 @@ def test_s_bias_within_2_sigma_of_reference_cpu_estimate():
     sigma = np.hypot(cpu_sem, gpu_sem)
     assert abs(gpu_mean - cpu_mean) < 2 * sigma + 0.05, (gpu_mean, gpu_sem, cpu_mean, cpu_sem)
     assert abs(gpu_mean - 3.571) < 0.3  # published-in-BASELINE.md survey value
+
+
+def test_ensemble_snapshot_resume_is_bit_identical():
+    """f4: run 4 iterations straight vs 2 + snapshot + fresh engine + restore + 2."""
+    p = transition_params("test", 0)
+    R = 37
+    with _ensemble(p, R, seed=(11, 12)) as e:
+        e.run(PHASE_EQ, 0, 1)
+        e.init_config_from_positions()
+        e.reset_clocks()
+        e.run(PHASE_MAIN, 0, 4)
+        ref_pos, ref_cfg = e.get_positions(), e.get_config()
+    with _ensemble(p, R, seed=(11, 12)) as e:
+        e.run(PHASE_EQ, 0, 1)
+        e.init_config_from_positions()
+        e.reset_clocks()
+        e.run(PHASE_MAIN, 0, 2)
+        snap = e.snapshot()
+    with Engine(p, R) as e2:
+        e2.restore(snap)
+        e2.run(PHASE_MAIN, 2, 2)
+        assert np.array_equal(e2.get_positions().view(np.uint64), ref_pos.view(np.uint64))
+        assert np.array_equal(e2.get_config(), ref_cfg)
