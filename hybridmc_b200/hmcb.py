@@ -52,3 +52,46 @@ class File(_Group):
 
     def __exit__(self, *a):
         return False
+
+
+# chunk shapes / filters of the reference's writers (src/writer.h:14-220, src/config.cc:34-46)
+_REF_CHUNKS = {
+    "config/int": lambda shp: (1024,),
+    "unique_config/pos": lambda shp: (10,) + tuple(shp[1:]),
+    "unique_config/vel": lambda shp: (10,) + tuple(shp[1:]),
+    "unique_config/config": lambda shp: (1000,),
+    "config_count": lambda shp: (100,) + tuple(shp[1:]),
+    "dist": lambda shp: (10000,) + tuple(shp[1:]),
+}
+
+
+def to_hdf5(src, dst):
+    """Convert an HMCB container into a real HDF5 file with the reference's layout
+    (names, dtypes, unlimited first dimension, chunking, deflate 6 on pos/vel) so that the
+    reference's tools/*.py read it.  Needs h5py, which this image does not ship: run it
+    wherever the analysis tools run.  `python -m hybridmc_b200.hmcb in.h5 out.h5`."""
+    try:
+        import h5py
+    except ImportError as exc:  # pragma: no cover - h5py is absent from the build image
+        raise RuntimeError("to_hdf5 needs h5py (not installed here)") from exc
+    f = File(src)
+    with h5py.File(dst, "w") as out:
+        for name, val in dict.items(f):
+            if isinstance(val, str):
+                out.create_dataset(name, data=val, dtype=h5py.string_dtype())
+                continue
+            arr = np.asarray(val)
+            if name in _REF_CHUNKS and arr.ndim >= 1:
+                kw = dict(maxshape=(None,) + arr.shape[1:], chunks=_REF_CHUNKS[name](arr.shape))
+                if name in ("unique_config/pos", "unique_config/vel"):
+                    kw.update(compression="gzip", compression_opts=6)
+                out.create_dataset(name, data=arr, **kw)
+            else:
+                out.create_dataset(name, data=arr)
+        for name, val in f.attrs.items():
+            out.attrs[name] = val
+
+
+if __name__ == "__main__":
+    import sys
+    to_hdf5(sys.argv[1], sys.argv[2])
