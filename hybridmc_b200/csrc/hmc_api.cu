@@ -125,6 +125,17 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.nnear_min2 = p.nnear_min * p.nnear_min;
   a.nnear_max2 = p.nnear_max * p.nnear_max;
   a.rh2 = p.rh * p.rh;
+  a.s_in_tab[0] = a.near_min2;
+  a.s_in_tab[1] = a.nnear_min2;
+  a.s_in_tab[2] = a.rh2;
+  a.s_out_tab[0] = a.near_max2;
+  a.s_out_tab[1] = a.nnear_max2;
+  a.s_out_tab[2] = a.rh2;
+  a.sigma2_tab[0] = a.near_min2;
+  a.sigma2_tab[1] = a.near_max2;
+  a.sigma2_tab[2] = a.nnear_min2;
+  a.sigma2_tab[3] = a.nnear_max2;
+  a.sigma2_tab[4] = a.rh2;
   a.m = p.m;
   a.vsigma = std::sqrt(p.temp / p.m);
   a.del_t = p.del_t;

@@ -31,6 +31,10 @@ struct KArgs {
   int nb, ncell, npairs, nslots, nstates;
   double l, inv_l, lcell, inv_lcell;
   double near_min2, near_max2, nnear_min2, nnear_max2, rh2;
+  // lookup tables (constant-bank indexed loads instead of select chains)
+  double s_in_tab[3];   // inner radius^2 by pair class: nearest, next-nearest, nonlocal core
+  double s_out_tab[3];  // outer radius^2 by pair class (nonlocal entry unused)
+  double sigma2_tab[5]; // wall radius^2 by event type 0..4
   double m, vsigma; // vsigma = sqrt(temp/m), init_vel (hardspheres.cc:202)
   double del_t, del_t_wl, gamma0;
   uint32_t nsteps, nsteps_eq, nsteps_wl, write_step, mc_moves, mc_write;

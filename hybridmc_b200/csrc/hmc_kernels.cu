@@ -224,12 +224,12 @@ __device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, c
   if (!__any_sync(0xffffffffu, info != 0u)) {
     // no bonded / bondable pair among the 32 pairs of this pass — the common case:
     // local wells and plain hard cores only
-    const double s_in = local ? (near ? a.near_min2 : a.nnear_min2) : a.rh2;
+    const int cls = min(d, 3) - 1; // 0 nearest, 1 next-nearest, 2 nonlocal
+    const double s_in = a.s_in_tab[cls];
     inner = approaching && (rv2 > vv * (rr - s_in)); // t_until_inner_coll :217-240
-    s2 = inner ? s_in : (near ? a.near_max2 : a.nnear_max2);
+    s2 = inner ? s_in : a.s_out_tab[cls];
     outer_ok = local;
-    ty = local ? (near ? HMC_EV_MIN_NEAREST : HMC_EV_MIN_NNEAREST) + (inner ? 0u : 1u)
-               : unsigned(HMC_EV_MIN_NONLOCAL_INNER);
+    ty = unsigned(2 * cls) + ((inner || !local) ? 0u : 1u);
   } else {
     // nonlocal bond bookkeeping (info == 0 for local pairs)
     const unsigned tb = info & 0x7fu;
@@ -664,11 +664,7 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
     const unsigned long long tmask = tb ? (1ull << (tb - 1)) : 0ull;
     const double r2p = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
     // radius of the wall that was hit
-    double sigma2 = a.rh2;
-    sigma2 = ty == HMC_EV_MIN_NEAREST ? a.near_min2 : sigma2;
-    sigma2 = ty == HMC_EV_MAX_NEAREST ? a.near_max2 : sigma2;
-    sigma2 = ty == HMC_EV_MIN_NNEAREST ? a.nnear_min2 : sigma2;
-    sigma2 = ty == HMC_EV_MAX_NNEAREST ? a.nnear_max2 : sigma2;
+    double sigma2 = a.sigma2_tab[min(ty, 4u)];
     sigma2 = ty == HMC_EV_MAX_NONLOCAL_INNER ? r2p : sigma2; // :1462-1466
     if (ty == HMC_EV_MAX_NONLOCAL_OUTER)                     // :1548-1552
       sigma2 = (R.has_stair && (~R.config & tmask)) ? R.stair2 : r2p;
