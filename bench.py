@@ -260,10 +260,14 @@ def run_gpu_arm(args):
         return ms
 
     it = 0
+    def flush_l2():
+        flush.zero_()  # 256 MiB write > 126 MB L2
+        torch.cuda.synchronize()
+
     for _ in range(args.warmup):
         one_step(it)
         it += 1
-        flush.zero_()
+        flush_l2()
     # ---- device-resident timed region ----
     ev0 = e.get_event_counts()
     l0 = e.launch_stats()[0]
@@ -276,7 +280,7 @@ def run_gpu_arm(args):
     for _ in range(args.steps):
         kernel_ms.append(one_step(it))
         it += 1
-        flush.zero_()  # L2 flush between timed iterations (not part of kernel_ms)
+        flush_l2()  # between timed iterations; not part of kernel_ms
     barrier()
     wall = time.perf_counter() - t0
     if proc:
