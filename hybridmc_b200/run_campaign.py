@@ -51,7 +51,8 @@ def fmt(bits):
 
 
 def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, max_rounds=40,
-                 max_layers=None, hist_bins=2048, rank=0, world=1, log=print):
+                 max_layers=None, hist_bins=2048, rank=0, world=1, log=print, wl=True,
+                 eq_iters=None):
     os.makedirs(out_dir, exist_ok=True)
     layers = layers_of(master)
     jsons = {(fmt(t[1]), fmt(t[2])): t[3] for t in transition_jsons(master)}
@@ -74,7 +75,8 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
             out = run_transition_ensemble(params, [structures[t[0]] for t in todo], replicas,
                                           device=device, seed=(params[0].seeds[0], 1 + layer),
                                           iters_per_round=iters_per_round, max_rounds=max_rounds,
-                                          hist_bins=hist_bins, hist_rmax=rmax)
+                                          hist_bins=hist_bins, hist_rmax=rmax, wl=wl,
+                                          eq_iters=eq_iters)
             dt = time.time() - t0
             for k, (bits_in, bits_out, p) in enumerate(todo):
                 name = "hybridmc_%d_%s_%s" % (layer, fmt(bits_in), fmt(bits_out))
@@ -140,6 +142,9 @@ def main(argv=None):
     ap.add_argument("--iters-per-round", type=int, default=None)
     ap.add_argument("--max-rounds", type=int, default=40)
     ap.add_argument("--max-layers", type=int, default=None)
+    ap.add_argument("--no-wl", action="store_true", help="skip the per-replica Wang-Landau pre-estimate")
+    ap.add_argument("--eq-iters", type=int, default=None)
+    ap.add_argument("--hist-bins", type=int, default=2048)
     args = ap.parse_args(argv)
     with open(args.json) as f:
         master = json.load(f)
@@ -151,7 +156,8 @@ def main(argv=None):
         dist.init_process_group("gloo")  # host-side hand-off of structures only
     out_dir = args.out or os.path.splitext(os.path.basename(args.json))[0]
     summary, wall = run_campaign(master, out_dir, args.replicas, device, args.iters_per_round,
-                                 args.max_rounds, args.max_layers, rank=rank, world=world)
+                                 args.max_rounds, args.max_layers, hist_bins=args.hist_bins, rank=rank,
+                                 world=world, wl=not args.no_wl, eq_iters=args.eq_iters)
     print("rank %d: %d transitions in %.1f s -> %.0f transitions/hour" % (
         rank, len(summary), wall, 3600.0 * len(summary) / max(wall, 1e-9)))
 
