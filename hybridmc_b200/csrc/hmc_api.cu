@@ -475,18 +475,21 @@ int hmc_init_config_from_positions(hmc_handle h) {
     const double rc2 = p.rc * p.rc;
     const double *q = pos.data() + size_t(r) * h->nb * 3;
     uint64_t c = 0;
-    for (int i = 0; i + 3 < h->nb; i++)
-      for (int j = i + 3; j < h->nb; j++) {
-        const int k = bond_index(p.transient_bonds, p.n_transient, i, j);
-        if (k < 0) continue;
-        double dx = q[3 * j] - q[3 * i], dy = q[3 * j + 1] - q[3 * i + 1],
-               dz = q[3 * j + 2] - q[3 * i + 2];
-        dx -= std::round(dx * inv_l) * l;
-        dy -= std::round(dy * inv_l) * l;
-        dz -= std::round(dz * inv_l) * l;
-        const double d2 = dx * dx + dy * dy + dz * dz;
-        if (d2 < rc2) c ^= (uint64_t(1) << k);
-      }
+    // only pairs on the transient-bond list can set a bit; the first list entry of a
+    // pair owns it (std::find, config.h:34)
+    for (unsigned k = 0; k < p.n_transient; k++) {
+      uint32_t i = p.transient_bonds[k][0], j = p.transient_bonds[k][1];
+      normalise(i, j);
+      if (j < i + 3 || int(j) >= h->nb) continue;
+      if (bond_index(p.transient_bonds, p.n_transient, i, j) != int(k)) continue;
+      double dx = q[3 * j] - q[3 * i], dy = q[3 * j + 1] - q[3 * i + 1],
+             dz = q[3 * j + 2] - q[3 * i + 2];
+      dx -= std::round(dx * inv_l) * l;
+      dy -= std::round(dy * inv_l) * l;
+      dz -= std::round(dz * inv_l) * l;
+      const double d2 = dx * dx + dy * dy + dz * dz;
+      if (d2 < rc2) c ^= (uint64_t(1) << k);
+    }
     cfg[r] = c;
   }
   return hmc_set_config(h, cfg.data());
