@@ -143,3 +143,40 @@ def test_negative_and_backward_clock_is_rejected():
         e.md_steps_injected(PHASE_EQ, 3, o.normals(1)[None])
         with pytest.raises(Exception):
             e.md_steps_injected(PHASE_EQ, 1, o.normals(1)[None])
+
+
+def test_no_bonds_and_zero_length_step():
+    """edge cases: a chain without any nonlocal bond (nstates = 1, empty dist rows), and
+    step index 0 (step_time = 0: only t <= 0 events — bead 0 starts on a cell wall)."""
+    p = params_from_json(load_config("8bead_1bond", nonlocal_bonds=[], transient_bonds=[]))
+    tr = _trace_pair(p, 3)
+    assert len(tr) > 100
+    o = OracleRun(p)
+    pos = o.init_pos()
+    o.sim.init_s()
+    o.sim.reset_clocks()
+    o.sim.enable_trace(64)
+    nrm = o.normals(1)
+    assert o.sim.md_step(PHASE_MAIN, 0, nrm[0]) == 0
+    otr, on = o.sim.get_trace()
+    with Engine(p, 1) as e:
+        e.set_positions(pos[None])
+        e.init_s()
+        e.reset_clocks()
+        e.enable_trace(0, 64)
+        e.enable_samples(4, 4)
+        e.md_steps_injected(PHASE_MAIN, 0, nrm[None])
+        gtr, gn = e.get_trace()
+        assert gn == on and first_trace_mismatch(otr, gtr) is None
+        assert all(t <= 0.0 for t in gtr["t"])
+        dist, nrows = e.get_dist()
+        assert int(nrows[0]) == 1  # a dist row is appended even for the zero-length step
+        cc, _, _, err = e.get_counts()
+        assert int(cc.sum()) == 1 and err[0] == 0  # step 0 is recorded (0 % write_step == 0)
+
+
+def test_maximum_chain_length():
+    """HMC_MAX_BEADS = 64 beads (2 080 event-table slots, 2 partner passes per bead)"""
+    d = load_config("50bead_9bond")
+    d.update(nbeads=64, transient_bonds=[[1, 9]], permanent_bonds=[], length=48.0, ncell=10)
+    _trace_pair(params_from_json(d), 2, phase=PHASE_EQ)
