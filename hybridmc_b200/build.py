@@ -18,8 +18,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhybridmc_b200.so")
-SOURCES = ["hmc_kernels.cu", "hmc_api.cu", "hmc_host.cu", "hmc_program.cu"]
-HEADERS = [os.path.join(CSRC, "hmc_internal.h"),
+SOURCES = ["hmc_kernels.cu", "hmc_api.cu", "hmc_host.cu", "hmc_program.cu", "hmc_h5.cu"]
+HEADERS = [os.path.join(CSRC, "hmc_internal.h"), os.path.join(CSRC, "host", "h5lite.h"),
            os.path.join(os.path.dirname(HERE), "include", "hybridmc_b200.h")]
 
 

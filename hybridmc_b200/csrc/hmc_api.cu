@@ -15,6 +15,7 @@
 namespace {
 thread_local std::string g_create_error;
 }
+void hmc_set_global_error(const char *msg) { g_create_error = msg; }
 
 struct hmc_engine {
   int device = 0;

@@ -97,4 +97,7 @@ cudaError_t hmc_launch(const KArgs &a, int group, cudaStream_t stream, int *grid
 size_t hmc_smem_per_replica(int nb);
 int hmc_pick_group(int nb);
 
+// message returned by hmc_last_error(NULL) (handle-less entry points)
+void hmc_set_global_error(const char *msg);
+
 #endif

@@ -8,12 +8,14 @@
 // executable.  New optional flags (all default off, so the campaign driver's command
 // lines run unchanged): --device D.
 //
-// Output: the image has no libhdf5, so datasets go to a small self-describing container
-// ("HMCB", see hybridmc_b200/hmcb.py for the reader) holding exactly the reference's
-// dataset / attribute names and shapes (src/writer.h, src/config.cc:34-60,
-// src/main.cc:383-409,443-446).  The writer sits behind one class so that an HDF5 back
-// end can replace it.
+// Output: HDF5 with exactly the reference's dataset / attribute names, types and shapes
+// (src/writer.h, src/config.cc:34-60, src/main.cc:383-409,443-446; snapshot:
+// src/snapshot.cc:14-68), written by the dependency-free writer in h5lite.h (the image
+// has no libhdf5).  --output-format hmcb selects the small self-describing container of
+// earlier builds (hybridmc_b200/hmcb.py); input and snapshot files of either kind are
+// recognised by their signature.
 #include "../../../include/hybridmc_b200.h"
+#include "h5lite.h"
 #include "mini_json.h"
 
 #include <cerrno>
@@ -31,6 +33,9 @@ namespace {
 
 // ------------------------------------------------------------------ container --
 enum DType : uint8_t { F64 = 0, F32 = 1, U64 = 2, U32 = 3, STR = 4 };
+static_assert(F64 == h5lite::F64 && F32 == h5lite::F32 && U64 == h5lite::U64 &&
+                  U32 == h5lite::U32 && STR == h5lite::VSTR,
+              "container and HDF5 type codes must coincide");
 
 class Container {
 public:
@@ -71,6 +76,17 @@ public:
     append(name, dt, row_dims, "", 0, 0);
   }
   bool write(const std::string &path, bool do_fsync) const {
+    return hdf5 ? write_hdf5(path, do_fsync) : write_hmcb(path, do_fsync);
+  }
+  bool write_hdf5(const std::string &path, bool do_fsync) const {
+    h5lite::Writer w; // DType values coincide with h5lite::Type (STR = VSTR)
+    for (auto &r : recs) {
+      if (r.kind == 0) w.dataset(r.name, r.dtype, r.dims, r.bytes.data(), r.bytes.size());
+      else w.attribute(r.name, r.dtype, r.dims, r.bytes.data(), r.bytes.size());
+    }
+    return w.write(path, do_fsync);
+  }
+  bool write_hmcb(const std::string &path, bool do_fsync) const {
     FILE *f = std::fopen(path.c_str(), "wb");
     if (!f) return false;
     std::fwrite("HMCB1\n", 1, 6, f);
@@ -92,6 +108,16 @@ public:
     return std::fclose(f) == 0;
   }
   bool read(const std::string &path) {
+    if (h5lite::Reader::is_hdf5(path)) {
+      h5lite::Reader r;
+      if (!r.open(path)) return false;
+      recs.clear();
+      for (auto &kv : r.datasets)
+        recs.push_back(Rec{0, kv.first, kv.second.dtype, kv.second.dims, kv.second.bytes});
+      for (auto &kv : r.attrs)
+        recs.push_back(Rec{1, kv.first, kv.second.dtype, kv.second.dims, kv.second.bytes});
+      return true;
+    }
     std::ifstream in(path, std::ios::binary);
     if (!in) return false;
     char magic[6];
@@ -119,6 +145,7 @@ public:
     }
     return true;
   }
+  bool hdf5 = true;
   const Rec *find(const std::string &name, uint8_t kind = 0) const {
     for (auto &r : recs)
       if (r.name == name && r.kind == kind) return &r;
@@ -246,6 +273,7 @@ void on_snapshot(void *u, const double *pos, const double *sb, int ns, uint64_t 
   // write_snapshot (snapshot.cc:14-68): pos, s_bias [nstates,1], mt, attr config;
   // temporary file + fsync + atomic rename (main.cc:480-486)
   Container s;
+  s.hdf5 = o->file.hdf5;
   s.put(0, "pos", F64, {o->p.nbeads, 3}, pos, sizeof(double) * 3 * o->p.nbeads);
   s.put(0, "s_bias", F64, {uint64_t(ns), 1}, sb, sizeof(double) * ns);
   s.put(0, "mt", STR, {}, mt_state, std::strlen(mt_state));
@@ -264,10 +292,11 @@ void usage() {
                "allowed options:\n"
                "  -h [ --help ]         produce help message\n"
                "  --json-file arg       json\n"
-               "  --output-file arg     output (HMCB container with the reference's dataset names)\n"
+               "  --output-file arg     output (HDF5, the reference's dataset names)\n"
                "  --input-file arg      input: unique_config/pos of a previous layer\n"
                "  --snapshot-file arg   snapshot\n"
-               "  --device arg (=0)     CUDA device\n";
+               "  --device arg (=0)     CUDA device\n"
+               "  --output-format arg (=hdf5)  hdf5 | hmcb\n";
 }
 
 } // namespace
@@ -280,6 +309,7 @@ int main(int argc, char *argv[]) {
   std::vector<std::string> positional;
   std::string input_name, snapshot_name;
   int device = 0;
+  bool hdf5 = true;
   try {
     for (int i = 1; i < argc; i++) {
       std::string a = argv[i], val;
@@ -305,6 +335,11 @@ int main(int argc, char *argv[]) {
       else if (take("json-file")) positional.insert(positional.begin(), val);
       else if (take("output-file")) positional.push_back(val);
       else if (take("device")) device = std::atoi(val.c_str());
+      else if (take("output-format")) {
+        if (val != "hdf5" && val != "hmcb")
+          throw std::runtime_error("the argument ('" + val + "') for option '--output-format' is invalid");
+        hdf5 = val == "hdf5";
+      }
       else if (a.size() > 1 && a[0] == '-') throw std::runtime_error("unrecognised option '" + a + "'");
       else positional.push_back(a);
     }
@@ -328,6 +363,7 @@ int main(int argc, char *argv[]) {
 
     Output out;
     out.p = p;
+    out.file.hdf5 = hdf5;
     out.snapshot_name = snapshot_name;
     out.nstates = 1u << p.n_transient;
     // datasets exist from the start, as in main.cc:385-394 (config_count gets a zero row)

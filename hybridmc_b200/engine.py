@@ -37,6 +37,7 @@ EXPORTS = [
     "hmc_get_moves_done", "hmc_init_pos_engine", "hmc_run_program_exact",
     "hmc_run_program_exact_sink", "hmc_get_schedule_state", "hmc_set_schedule_state",
     "hmc_set_s_bias_per_replica",
+    "hmc_h5_create", "hmc_h5_dataset", "hmc_h5_attribute", "hmc_h5_write", "hmc_h5_destroy",
 ]
 
 _lib = None

@@ -3,8 +3,8 @@
 a lattice layer runs as ONE GPU ensemble, layers run in order, and each transition leaves
 the files the reference leaves, with the reference's names
 (`hybridmc_<layer>_<bits_in>_<bits_out>.{json,h5,log}`, tools/init_json.py:109-125), so
-`diff_s_bias.py`-style collection works on the result.  `.h5` files are HMCB containers
-(hybridmc_b200/hmcb.py) with the reference's dataset names until an HDF5 back end exists.
+`diff_s_bias.py`-style collection works on the result.  `.h5` files are HDF5 with the
+reference's dataset names (hybridmc_b200/output.py, written by the library's own writer).
 
   python -m hybridmc_b200.run_campaign master.json [--replicas R] [--out DIR] [--device D]
                                        [--iters-per-round K] [--max-rounds N] [--max-layers L]
@@ -17,7 +17,6 @@ import argparse
 import csv
 import json
 import os
-import struct
 import sys
 import time
 
@@ -25,24 +24,12 @@ import numpy as np
 
 from .campaign import layers_of, run_transition_ensemble, shard
 from .engine import init_pos_chain
+from .output import File, write_hdf5
 from .params import transition_jsons
 
-_DT = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.uint64): 2,
-       np.dtype(np.uint32): 3}
-
-
-def write_hmcb(path, datasets, attrs):
-    """same container as the executable writes (csrc/host/hybridmc_main.cpp)"""
-    with open(path + ".tmp", "wb") as f:
-        f.write(b"HMCB1\n")
-        for kind, items in ((0, datasets), (1, attrs)):
-            for name, arr in items.items():
-                arr = np.ascontiguousarray(arr)
-                f.write(struct.pack("<BH", kind, len(name)) + name.encode())
-                f.write(struct.pack("<BB", _DT[arr.dtype], arr.ndim))
-                f.write(struct.pack("<%dQ" % arr.ndim, *arr.shape))
-                raw = arr.tobytes()
-                f.write(struct.pack("<Q", len(raw)) + raw)
+def write_output(path, datasets, attrs):
+    """HDF5 through the library's writer, temporary file + rename as main.cc:383,495"""
+    write_hdf5(path + ".tmp", datasets, attrs)
     os.replace(path + ".tmp", path)
 
 
@@ -93,7 +80,7 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                       "nonlocal_bonds": np.array(p.bond_list("nonlocal"), np.uint32).reshape(-1, 2),
                       "transient_bonds": np.array(p.bond_list("transient"), np.uint32).reshape(-1, 2),
                       "permanent_bonds": np.array(p.bond_list("permanent"), np.uint32).reshape(-1, 2)}
-                write_hmcb(os.path.join(out_dir, name + ".h5"), ds, at)
+                write_output(os.path.join(out_dir, name + ".h5"), ds, at)
                 with open(os.path.join(out_dir, name + ".log"), "w") as f:
                     f.write("replicas %d rounds %d accepted %s s_bias %s counts %s\n" % (
                         replicas, out["rounds"][k], bool(out["accepted"][k]),
@@ -111,7 +98,6 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                 continue
             path = os.path.join(out_dir, "hybridmc_%d_%s_%s.h5" % (layer, fmt(bits_in), fmt(bits_out)))
             if os.path.exists(path):
-                from .hmcb import File
                 up = File(path)["unique_config"]["pos"]
                 if len(up):
                     new_structs.setdefault(bits_out, np.array(up[0]))

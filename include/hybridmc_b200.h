@@ -347,6 +347,32 @@ int hmc_set_schedule_state(hmc_handle h, const hmc_schedule_state *in);
  * per-transition broadcast of hmc_set_s_bias loses per-replica values mid-WL). */
 int hmc_set_s_bias_per_replica(hmc_handle h, const double *s_bias, int nstates);
 
+/* ---- HDF5 output -----------------------------------
+ * Dependency-free writer of the HDF5 files the reference produces through H5Cpp
+ * (datasets: src/writer.h, src/config.cc:34-60; root attributes: src/main.cc:397-409,
+ * src/config.cc:18-27; snapshot: src/snapshot.cc:14-68).  Items are collected in memory
+ * and the file is written once by hmc_h5_write (superblock v0, symbol-table groups,
+ * contiguous datasets: readable by every libhdf5 / h5py).  `path` may contain '/'
+ * (groups are created on demand, as H5File::createGroup in main.cc:387).  dims == NULL
+ * or rank 0 is a scalar; nbytes must equal prod(dims) * element size; HMC_H5_VSTR is a
+ * scalar variable-length string (data = the characters, nbytes = their count).
+ * Errors: <0, message in hmc_last_error(NULL). */
+typedef enum hmc_h5_type {
+  HMC_H5_F64 = 0, /* H5::PredType::NATIVE_DOUBLE */
+  HMC_H5_F32 = 1, /* NATIVE_FLOAT  (s_bias, main.cc:409) */
+  HMC_H5_U64 = 2, /* NATIVE_UINT64 (config, config_count) */
+  HMC_H5_U32 = 3, /* NATIVE_UINT   (nsteps, bond lists) */
+  HMC_H5_VSTR = 4 /* H5::StrType(0, H5T_VARIABLE) (snapshot.cc:44) */
+} hmc_h5_type;
+typedef struct hmc_h5_file *hmc_h5;
+int hmc_h5_create(hmc_h5 *out);
+int hmc_h5_dataset(hmc_h5 f, const char *path, int dtype, int rank, const uint64_t *dims,
+                   const void *data, uint64_t nbytes);
+int hmc_h5_attribute(hmc_h5 f, const char *name, int dtype, int rank, const uint64_t *dims,
+                     const void *data, uint64_t nbytes);
+int hmc_h5_write(hmc_h5 f, const char *filename, int do_fsync);
+int hmc_h5_destroy(hmc_h5 f);
+
 /* ---- launch statistics (for bench.py) ------------------------------------ */
 
 /* kernels launched by this handle so far, and the device time (ms, CUDA

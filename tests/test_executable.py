@@ -60,7 +60,7 @@ def test_fails_loudly_without_gpu(tmp_path):
 
 @pytest.mark.gpu
 def test_outputs_match_oracle_and_layer_handoff(tmp_path, oracle):
-    from hybridmc_b200.hmcb import File
+    from hybridmc_b200.output import File
     from oracle_lib import OrcMainResult
     trans = transition_jsons(load_config("test"))
     # layer 0: bond [2,6] transient
@@ -78,6 +78,8 @@ def test_outputs_match_oracle_and_layer_handoff(tmp_path, oracle):
     n_o = C.c_uint(0)
     assert oracle.orc_run_main(C.byref(p0), None, 0, len(dist_o), dist_o.ctypes.data_as(C.c_void_p),
                                C.byref(n_o), C.byref(ro)) == 0
+    from hybridmc_b200 import h5lite
+    assert h5lite.is_hdf5(str(out0))
     with File(str(out0)) as f:
         assert np.array_equal(f["s_bias"], np.array(list(ro.s_bias)[:2], dtype=np.float32))
         cc = f["config_count"]
@@ -110,7 +112,7 @@ def test_outputs_match_oracle_and_layer_handoff(tmp_path, oracle):
 
 @pytest.mark.gpu
 def test_snapshot_resume(tmp_path):
-    from hybridmc_b200.hmcb import File
+    from hybridmc_b200.output import File
     d = dict(load_config("8bead_1bond"), total_iter=20, total_iter_eq=4, max_g_test_count=2)
     j = tmp_path / "c.json"
     j.write_text(json.dumps(d))
@@ -125,3 +127,21 @@ def test_snapshot_resume(tmp_path):
     assert r.returncode == 0, r.stderr
     with File(str(tmp_path / "b.h5")) as f:
         assert np.isfinite(f["s_bias"]).all()
+
+
+@pytest.mark.gpu
+def test_hmcb_and_hdf5_outputs_hold_the_same_data(tmp_path):
+    from hybridmc_b200 import h5lite
+    from hybridmc_b200.output import File
+    d = dict(load_config("8bead_1bond"), total_iter=12, total_iter_eq=3, max_g_test_count=2)
+    j = tmp_path / "c.json"
+    j.write_text(json.dumps(d))
+    assert run([str(j), str(tmp_path / "a.h5")]).returncode == 0
+    assert run([str(j), str(tmp_path / "a.hmcb"), "--output-format", "hmcb"]).returncode == 0
+    assert h5lite.is_hdf5(str(tmp_path / "a.h5")) and not h5lite.is_hdf5(str(tmp_path / "a.hmcb"))
+    a, b = File(str(tmp_path / "a.h5")), File(str(tmp_path / "a.hmcb"))
+    assert sorted(a) == sorted(b) and sorted(a.attrs) == sorted(b.attrs)
+    for k in a:
+        assert np.asarray(a[k]).dtype == np.asarray(b[k]).dtype and np.array_equal(a[k], b[k]), k
+    for k in a.attrs:
+        assert np.array_equal(a.attrs[k], b.attrs[k]), k
