@@ -35,6 +35,7 @@ struct hmc_engine {
   // device buffers
   TransDev *d_trans = nullptr;
   uint8_t *d_pairinfo = nullptr;
+  unsigned long long *d_bondmask = nullptr;
   uchar2 *d_pair_ij = nullptr;
   double *d_pos = nullptr, *d_vel = nullptr, *d_sbias = nullptr;
   uint64_t *d_config = nullptr;
@@ -150,6 +151,7 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.mc_write = p.mc_write;
   a.trans = h->d_trans;
   a.pairinfo = h->d_pairinfo;
+  a.bondmask = h->d_bondmask;
   a.pair_ij = h->d_pair_ij;
   a.n_replicas = h->R;
   a.replicas_per_trans = h->Rper;
@@ -185,6 +187,13 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.work_counter = h->d_work;
   a.smem_per_replica = uint32_t(hmc_smem_per_replica(h->nb));
   a.short_chain = (double(h->nb - 1) * p.near_max < 1.45 * p.length) ? 1 : 0;
+  {
+    const char *tp = getenv("HMC_TWO_PASS"); // experiment switch: 0 / 1 overrides the heuristic
+    // needs: one-image wrap (short chain) and partners in adjacent cells closer than half a
+    // box in every axis (ncell >= 5), so that single precision picks the same image
+    const bool can = a.short_chain && p.ncell >= 5;
+    a.two_pass = (tp ? atoi(tp) != 0 : h->nb >= 16) && can;
+  }
   a.max_events_per_step = 1u << 18; // ~30x the largest step of the shipped configs
 }
 
@@ -345,6 +354,7 @@ int hmc_create(const hmc_params *tr, int n_transitions, int replicas_per_transit
   for (int i = 0, q = 0; i < nb; i++)
     for (int j = i + 1; j < nb; j++, q++) pair_ij[q] = make_uchar2((unsigned char)i, (unsigned char)j);
   std::vector<uint8_t> pairinfo(size_t(h->T) * np, 0);
+  std::vector<unsigned long long> bondmask(size_t(h->T) * nb, 0ull);
   std::vector<TransDev> trans(h->T);
   for (int t = 0; t < h->T; t++) {
     const hmc_params &p = tr[t];
@@ -373,6 +383,10 @@ int hmc_create(const hmc_params *tr, int n_transitions, int replicas_per_transit
         if (tbk >= 0) info |= uint8_t(tbk + 1);
         if (pbk >= 0) info |= 0x80u;
         pairinfo[size_t(t) * np + q] = info;
+        if (info) {
+          bondmask[size_t(t) * nb + i] |= 1ull << j;
+          bondmask[size_t(t) * nb + j] |= 1ull << i;
+        }
         if (bond_index(p.nonlocal_bonds, p.n_nonlocal, i, j) >= 0 && nl < HMC_MAX_BONDS) {
           d.nl_i[nl] = uint8_t(i);
           d.nl_j[nl] = uint8_t(j);
@@ -386,6 +400,9 @@ int hmc_create(const hmc_params *tr, int n_transitions, int replicas_per_transit
   CKC(cudaMemcpy(h->d_trans, trans.data(), sizeof(TransDev) * h->T, cudaMemcpyHostToDevice));
   CKC(dalloc(&h->d_pairinfo, pairinfo.size()));
   CKC(cudaMemcpy(h->d_pairinfo, pairinfo.data(), pairinfo.size(), cudaMemcpyHostToDevice));
+  CKC(dalloc(&h->d_bondmask, bondmask.size()));
+  CKC(cudaMemcpy(h->d_bondmask, bondmask.data(), sizeof(unsigned long long) * bondmask.size(),
+                 cudaMemcpyHostToDevice));
   CKC(dalloc(&h->d_pair_ij, size_t(np)));
   CKC(cudaMemcpy(h->d_pair_ij, pair_ij.data(), sizeof(uchar2) * np, cudaMemcpyHostToDevice));
 
@@ -411,7 +428,7 @@ int hmc_destroy(hmc_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void *bufs[] = {h->d_trans,    h->d_pairinfo,  h->d_pair_ij,    h->d_pos,        h->d_vel,
+  void *bufs[] = {h->d_bondmask, h->d_trans,    h->d_pairinfo,  h->d_pair_ij,    h->d_pos,        h->d_vel,
                   h->d_sbias,    h->d_config,    h->d_err,        h->d_acc,        h->d_dist,
                   h->d_dist_n,   h->d_cfg_int,   h->d_cfg_n,      h->d_hist,       h->d_uniq_pos,
                   h->d_uniq_vel, h->d_uniq_found, h->d_trace,     h->d_trace_n,    h->d_work,

@@ -41,6 +41,7 @@ struct KArgs {
   // tables
   const TransDev *trans;
   const uint8_t *pairinfo; // [T][npairs]: bits 0-6 transient bit index+1, bit 7 permanent
+  const unsigned long long *bondmask; // [T][nb]: bit k set iff pairinfo of (b,k) is non-zero
   const uchar2 *pair_ij;   // [npairs] -> (i,j), i<j
   // ensemble
   int n_replicas, replicas_per_trans;
@@ -89,6 +90,7 @@ struct KArgs {
   uint32_t smem_per_replica;
   uint32_t max_events_per_step;
   int short_chain; // (nb-1)*near_max < 1.45*length: bead-bead differences stay below 1.5 boxes
+  int two_pass;    // partner re-prediction as pre-filter + compacted exact pass (chains >= 16 beads)
 };
 
 // launcher implemented in hmc_kernels.cu; group = lanes per replica (8/16/32)

@@ -62,6 +62,7 @@ struct Smem {
   double *b;   // [nb][BSTRIDE]
   double *evt; // [nslots]
   uint8_t *evty;
+  uint8_t *plist;           // [2 nb]: partners that survive the single-precision pre-filter
   const uint16_t *slot_row; // [nb]: slot(lo,hi) = slot_row[lo] + hi (CTA-shared)
   int nb;
 };
@@ -73,6 +74,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const uint16_t *slot_
   s.b = d;
   s.evt = d + BSTRIDE * nb;
   s.evty = reinterpret_cast<uint8_t *>(d + BSTRIDE * nb + nslots);
+  s.plist = s.evty + nslots;
   s.slot_row = slot_row;
   s.nb = nb;
   return s;
@@ -94,6 +96,7 @@ struct Rep {
   unsigned long long config;
   const TransDev *tr;
   const uint8_t *pinfo;  // pairinfo row of this replica's transition
+  const unsigned long long *bmask; // bondmask row
   double *sb;            // s_bias of this replica (global)
   double rc2, stair2, p_rc2;
   unsigned has_stair, has_p_rc, max_nbonds;
@@ -789,37 +792,173 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
       int far = int((cb0 >> (8 * axis)) & 0xffu) + ((wall & 1u) ? -1 : 1);
       far = far < 0 ? far + nc : (far >= nc ? far - nc : far);
       const unsigned others = 0x00ffffffu & ~(0xffu << (8 * axis)); // the two other axes
-      const int nitem = nbead * nb;
-      // warp-uniform trip count: 2*nb unless every group of the warp has a crossing
-      const int nloop = warp_any<G>(has && !is_cell) ? 2 * nb : nb;
-      for (int base = 0; base < nloop; base += G) {
-        const int idx = base + lane;
-        const bool second = idx >= nb;
-        const int b = second ? bj : bi;
-        int k = second ? idx - nb : idx;
-        const bool in_range = idx < nitem;
-        k = in_range ? k : b;
-        const int d = abs(b - k);
-        // nb + pair index; an in-range dummy for k == b (never stored)
-        const int slot = k == b ? nb : int(s.slot_row[min(b, k)]) + max(b, k);
-        const unsigned cb = second ? cb1 : cb0, ck = BCELL(s, k);
-        const unsigned am = adj_mask(cb, ck, ncm1x3);
-        // which (b,k) the reference predicts at this event
-        const bool want_cell = d >= 3 && int((ck >> (8 * axis)) & 0xffu) == far &&
-                               (am & others) == others;
-        const bool want_coll = d < 3 || (am & 0x00ffffffu) == 0x00ffffffu;
-        const bool active = has && in_range && k != b;
-        const bool doit = active && (is_cell ? want_cell : want_coll);
-        double tt;
-        const unsigned pty =
-            predict_pair(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), doit, tt);
-        const bool have = doit && pty != 0xffu;
-        const double tnew = have ? tt : CUDART_INF;
-        // collision: overwrite (or clear) the slot; crossing: keep the earlier of old/new
-        const bool store = active && (is_cell ? (have && tnew < s.evt[slot]) : true);
-        if (store) {
-          s.evt[slot] = tnew;
-          s.evty[slot] = uint8_t(pty);
+      if (!a.two_pass) {
+        // short chains: a single pass over all 2 nb candidates (the pre-filter below costs
+        // more than the few predictions it would save)
+        const int nitem = nbead * nb;
+        // warp-uniform trip count: 2*nb unless every group of the warp has a crossing
+        const int nloop = warp_any<G>(has && !is_cell) ? 2 * nb : nb;
+        for (int base = 0; base < nloop; base += G) {
+          const int idx = base + lane;
+          const bool second = idx >= nb;
+          const int b = second ? bj : bi;
+          int k = second ? idx - nb : idx;
+          const bool in_range = idx < nitem;
+          k = in_range ? k : b;
+          const int d = abs(b - k);
+          // nb + pair index; an in-range dummy for k == b (never stored)
+          const int slot = k == b ? nb : int(s.slot_row[min(b, k)]) + max(b, k);
+          const unsigned cb = second ? cb1 : cb0, ck = BCELL(s, k);
+          const unsigned am = adj_mask(cb, ck, ncm1x3);
+          // which (b,k) the reference predicts at this event
+          const bool want_cell = d >= 3 && int((ck >> (8 * axis)) & 0xffu) == far &&
+                                 (am & others) == others;
+          const bool want_coll = d < 3 || (am & 0x00ffffffu) == 0x00ffffffu;
+          const bool active = has && in_range && k != b;
+          const bool doit = active && (is_cell ? want_cell : want_coll);
+          double tt;
+          const unsigned pty =
+              predict_pair(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), doit, tt);
+          const bool have = doit && pty != 0xffu;
+          const double tnew = have ? tt : CUDART_INF;
+          // collision: overwrite (or clear) the slot; crossing: keep the earlier of old/new
+          const bool store = active && (is_cell ? (have && tnew < s.evt[slot]) : true);
+          if (store) {
+            s.evt[slot] = tnew;
+            s.evty[slot] = uint8_t(pty);
+          }
+        }
+      } else {
+        // Pass 1 — which (b,k) does the reference predict, and can the pair collide at all?
+        // Most candidates are plain nonlocal hard-core pairs (info == 0, |b-k| >= 3) whose
+        // only possible event is an inner collision at rh: approaching and
+        // rv^2 > vv (rr - rh^2) (if_coll :425-476).  A single-precision evaluation of the
+        // same quantities with rigorous error margins rejects the pairs that certainly fail
+        // that test (receding, or missing by more than the margin); their slot is cleared
+        // here.  Everything else — local wells, bond pairs, hits and near misses — goes to
+        // the exact double-precision prediction of pass 2, compacted so that its lanes are
+        // all busy.  A rejected pair has no event in exact arithmetic either, so the table
+        // is bit-identical to predicting every candidate.
+        // One lane per partner k; it is tested against both event beads, sharing its loads.
+        const float fl = float(a.l), finv_l = float(a.inv_l), frh2 = float(a.rh2);
+        const unsigned gshift = (threadIdx.x & 31u) & ~unsigned(G - 1);
+        const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+        const unsigned below = (1u << lane) - 1u;
+        const unsigned long long bm0 = __ldg(&R.bmask[bi]), bm1 = __ldg(&R.bmask[bj]);
+        int cnt = 0;
+        for (int base = 0; base < nb; base += G) {
+          const int kk = base + lane;
+          const bool kin = kk < nb;
+          const int k = kin ? kk : 0;
+          const unsigned ck = BCELL(s, k);
+          const double2 *rk = reinterpret_cast<const double2 *>(s.b + BSTRIDE * k);
+          const double2 k0 = rk[0], k1 = rk[1], k2 = rk[2];
+          const float dtf = float(t - BT(s, k));
+          const float wx = float(k1.y), wy = float(k2.x), wz = float(k2.y);
+          const float W = fabsf(wx) + fabsf(wy) + fabsf(wz);
+          const float Wd = fmaf(W, dtf, fl);
+  #pragma unroll
+          for (int q = 0; q < 2; q++) {
+            const int b = q ? bj : bi;
+            const unsigned cb = q ? cb1 : cb0;
+            const int d = abs(b - k);
+            // nb + pair index (k == b: some other valid slot, never stored)
+            const int slot = int(s.slot_row[min(b, k)]) + max(b, k);
+            const unsigned am = adj_mask(cb, ck, ncm1x3);
+            // which (b,k) the reference predicts at this event
+            const bool want_cell = d >= 3 && int((ck >> (8 * axis)) & 0xffu) == far &&
+                                   (am & others) == others;
+            const bool want_coll = d < 3 || (am & 0x00ffffffu) == 0x00ffffffu;
+            const bool active = has && kin && k != b && (q == 0 || !is_cell);
+            const bool doit = active && (is_cell ? want_cell : want_coll);
+            bool keep = doit;
+#ifdef HMC_VERIFY_PREFILTER
+            bool flagged = false;
+#endif
+            { // (two_pass implies short_chain: the one-image wrap below needs |d/l| < 1.5)
+              const bool plain = (((q ? bm1 : bm0) >> k) & 1ull) == 0ull; // no bond bookkeeping
+              // separation at the partner's clock: subtract in double (unwrapped coordinates
+              // may be large), then everything else in single precision
+              float dx = float(k0.x - (q ? J.x : I.x));
+              float dy = float(k0.y - (q ? J.y : I.y));
+              float dz = float(k1.x - (q ? J.z : I.z));
+              const float ux = float(q ? J.vx : I.vx), uy = float(q ? J.vy : I.vy),
+                          uz = float(q ? J.vz : I.vz);
+              // magnitudes that bound every intermediate: X for lengths, V for speeds
+              const float X = fabsf(dx) + fabsf(dy) + fabsf(dz) + Wd;
+              const float V = W + fabsf(ux) + fabsf(uy) + fabsf(uz);
+              dx = fmaf(wx, dtf, dx);
+              dy = fmaf(wy, dtf, dy);
+              dz = fmaf(wz, dtf, dz);
+              // (a predicted pair sits in adjacent cells: |separation| <= 2 lcell <= 0.4 boxes
+              // per axis with ncell >= 5, far from the half-box where the image would flip)
+              const float tx = dx * finv_l, ty_ = dy * finv_l, tz = dz * finv_l;
+              dx -= copysignf(fabsf(tx) >= 0.5f ? fl : 0.0f, tx);
+              dy -= copysignf(fabsf(ty_) >= 0.5f ? fl : 0.0f, ty_);
+              dz -= copysignf(fabsf(tz) >= 0.5f ? fl : 0.0f, tz);
+              const float ex = wx - ux, ey = wy - uy, ez = wz - uz;
+              const float rv = fmaf(dx, ex, fmaf(dy, ey, dz * ez));
+              const float vv = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+              const float gap = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, -frh2)));
+              // error bounds with unit roundoff u = 6e-8: |d rv| <= 10 u X V,
+              // |d rr| <= 13 u X^2, |d (rv^2 - vv gap)| <= 42 u X^2 V^2; the margins below
+              // are 16-40 times larger
+              const float XV = X * V;
+              const bool far_apart = gap > 1e-5f * X * X;
+              const bool receding = rv > 1e-5f * XV;
+              const bool misses = fmaf(rv, rv, -vv * gap) < -1e-4f * XV * XV;
+              const bool reject = d >= 3 && plain && far_apart && (receding || misses);
+#ifdef HMC_VERIFY_PREFILTER
+              flagged = doit && reject; // predict it anyway; pass 2 checks it has no event
+#else
+              keep = doit && !reject;
+#endif
+            }
+            // collision: every slot of bi / bj that is not (re)predicted is cleared
+            if (active && !is_cell && !keep) {
+              s.evt[slot] = CUDART_INF;
+              s.evty[slot] = 0xffu;
+            }
+            const unsigned gbits = (__ballot_sync(0xffffffffu, keep) >> gshift) & gmask;
+#ifdef HMC_VERIFY_PREFILTER
+            if (keep) s.plist[cnt + __popc(gbits & below)] = uint8_t((k + q * nb) | (flagged ? 0x80 : 0));
+#else
+            if (keep) s.plist[cnt + __popc(gbits & below)] = uint8_t(k + q * nb);
+#endif
+            cnt += __popc(gbits);
+          }
+        }
+        __syncwarp();
+
+        // Pass 2 — exact prediction of the surviving pairs
+        for (int base = 0; warp_any<G>(base < cnt); base += G) {
+          const int e = base + lane;
+          const bool on = e < cnt;
+#ifdef HMC_VERIFY_PREFILTER
+          const int raw = on ? int(s.plist[e]) : 0;
+          const int idx = raw & 0x7f;
+#else
+          const int idx = on ? int(s.plist[e]) : 0;
+#endif
+          const bool second = idx >= nb;
+          const int b = second ? bj : bi;
+          const int k = on ? (second ? idx - nb : idx) : b;
+          const int d = abs(b - k);
+          const int slot = k == b ? nb : int(s.slot_row[min(b, k)]) + max(b, k);
+          double tt;
+          const unsigned pty =
+              predict_pair(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), on, tt);
+          const bool have = on && pty != 0xffu;
+#ifdef HMC_VERIFY_PREFILTER
+          if (have && (raw & 0x80)) R.err |= 0x40000000u; // the pre-filter rejected a real event
+#endif
+          const double tnew = have ? tt : CUDART_INF;
+          // collision: overwrite (or clear) the slot; crossing: keep the earlier of old/new
+          const bool store = on && (is_cell ? (have && tnew < s.evt[slot]) : true);
+          if (store) {
+            s.evt[slot] = tnew;
+            s.evty[slot] = uint8_t(pty);
+          }
         }
       }
       __syncwarp();
@@ -1093,6 +1232,7 @@ template <int G> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hm
     const int trans = r / a.replicas_per_trans;
     R.tr = a.trans + trans;
     R.pinfo = a.pairinfo + size_t(trans) * a.npairs;
+    R.bmask = a.bondmask + size_t(trans) * a.nb;
     R.sb = a.s_bias + size_t(r) * a.nstates;
     R.config = a.config[r];
     R.rc2 = R.tr->rc2;
@@ -1295,7 +1435,7 @@ template <int G> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hm
 size_t hmc_smem_per_replica(int nb) {
   const size_t npairs = size_t(nb) * (nb - 1) / 2;
   const size_t nslots = nb + npairs;
-  size_t bytes = 8 * (size_t(BSTRIDE) * nb + nslots) + nslots;
+  size_t bytes = 8 * (size_t(BSTRIDE) * nb + nslots) + nslots + 2 * size_t(nb);
   return (bytes + 15) & ~size_t(15);
 }
 
