@@ -187,6 +187,7 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.work_counter = h->d_work;
   a.smem_per_replica = uint32_t(hmc_smem_per_replica(h->nb));
   a.short_chain = (double(h->nb - 1) * p.near_max < 1.45 * p.length) ? 1 : 0;
+  a.chain_max = double(h->nb - 1) * p.near_max;
   {
     const char *tp = getenv("HMC_TWO_PASS"); // experiment switch: 0 / 1 overrides the heuristic
     // needs: one-image wrap (short chain) and partners in adjacent cells closer than half a

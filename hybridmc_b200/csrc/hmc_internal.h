@@ -90,6 +90,7 @@ struct KArgs {
   uint32_t smem_per_replica;
   uint32_t max_events_per_step;
   int short_chain; // (nb-1)*near_max < 1.45*length: bead-bead differences stay below 1.5 boxes
+  double chain_max; // (nb-1)*near_max: the fully stretched chain
   int two_pass;    // partner re-prediction as pre-filter + compacted exact pass (chains >= 16 beads)
 };
 

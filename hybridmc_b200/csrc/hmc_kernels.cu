@@ -840,7 +840,24 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
         // all busy.  A rejected pair has no event in exact arithmetic either, so the table
         // is bit-identical to predicting every candidate.
         // One lane per partner k; it is tested against both event beads, sharing its loads.
-        const float fl = float(a.l), finv_l = float(a.inv_l), frh2 = float(a.rh2);
+        // The two tests of a lane (partner k against bi and against bj) are the same
+        // arithmetic on two data sets: they run as packed float2 operations (FFMA2 / FADD2
+        // / FMUL2 of sm_100), bi in .x and bj in .y.
+        const float fl = float(a.l);
+        const float2 invl2 = make_float2(float(a.inv_l), float(a.inv_l));
+        const float2 nl2 = make_float2(-fl, -fl);
+        const float2 nrh2 = make_float2(-float(a.rh2), -float(a.rh2));
+        const float2 magic = make_float2(12582912.0f, 12582912.0f); // 1.5 * 2^23: rint by adding
+        const float2 nmagic = make_float2(-12582912.0f, -12582912.0f);
+        // event-bead velocities (negated) and their 1-norms
+        const float2 nux = make_float2(-float(I.vx), -float(J.vx));
+        const float2 nuy = make_float2(-float(I.vy), -float(J.vy));
+        const float2 nuz = make_float2(-float(I.vz), -float(J.vz));
+        const float2 U = make_float2(fabsf(nux.x) + fabsf(nuy.x) + fabsf(nuz.x),
+                                     fabsf(nux.y) + fabsf(nuy.y) + fabsf(nuz.y));
+        // lengths: |x_k(t_k) - x_b(t)| <= stretched chain + |v_k| dt; one more |v_k| dt for the
+        // advance and one box for the wrap
+        const float Xc = float(a.chain_max) + fl;
         const unsigned gshift = (threadIdx.x & 31u) & ~unsigned(G - 1);
         const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
         const unsigned below = (1u << lane) - 1u;
@@ -856,8 +873,35 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
           const float dtf = float(t - BT(s, k));
           const float wx = float(k1.y), wy = float(k2.x), wz = float(k2.y);
           const float W = fabsf(wx) + fabsf(wy) + fabsf(wz);
-          const float Wd = fmaf(W, dtf, fl);
-  #pragma unroll
+          // magnitudes that bound every intermediate: X for lengths, V for speeds
+          const float X = fmaf(W + W, dtf, Xc);
+          const float2 XV = __fmul2_rn(make_float2(X, X), __fadd2_rn(make_float2(W, W), U));
+          const float far_min = 1e-5f * X * X;
+          // separation at the partner's clock: subtract in double (unwrapped coordinates
+          // may be large), then everything else in single precision
+          const float2 dt2 = make_float2(dtf, dtf);
+          const float2 wx2 = make_float2(wx, wx), wy2 = make_float2(wy, wy), wz2 = make_float2(wz, wz);
+          float2 dx = __ffma2_rn(wx2, dt2, make_float2(float(k0.x - I.x), float(k0.x - J.x)));
+          float2 dy = __ffma2_rn(wy2, dt2, make_float2(float(k0.y - I.y), float(k0.y - J.y)));
+          float2 dz = __ffma2_rn(wz2, dt2, make_float2(float(k1.x - I.z), float(k1.x - J.z)));
+          // minimum image, d - l rint(d/l).  (A predicted pair sits in adjacent cells:
+          // |separation| <= 2 lcell <= 0.4 boxes per axis with ncell >= 5, far from the
+          // half-box where the rounding mode or a single-precision error could matter.)
+          dx = __ffma2_rn(__fadd2_rn(__ffma2_rn(dx, invl2, magic), nmagic), nl2, dx);
+          dy = __ffma2_rn(__fadd2_rn(__ffma2_rn(dy, invl2, magic), nmagic), nl2, dy);
+          dz = __ffma2_rn(__fadd2_rn(__ffma2_rn(dz, invl2, magic), nmagic), nl2, dz);
+          const float2 ex = __fadd2_rn(wx2, nux), ey = __fadd2_rn(wy2, nuy), ez = __fadd2_rn(wz2, nuz);
+          const float2 rv = __ffma2_rn(dx, ex, __ffma2_rn(dy, ey, __fmul2_rn(dz, ez)));
+          const float2 vv = __ffma2_rn(ex, ex, __ffma2_rn(ey, ey, __fmul2_rn(ez, ez)));
+          const float2 gap = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, nrh2)));
+          // error bounds with unit roundoff u = 6e-8: |d rv| <= 10 u X V, |d rr| <= 13 u X^2,
+          // |d (rv^2 - vv gap)| <= 42 u X^2 V^2; the margins are 16-40 times larger:
+          // receding: rv > 1e-5 XV;  misses: rv^2 + 1e-4 (XV)^2 < vv gap
+          const float2 rv_min = __fmul2_rn(XV, make_float2(1e-5f, 1e-5f));
+          const float2 xvs = __fmul2_rn(XV, make_float2(1e-2f, 1e-2f));
+          const float2 lhs = __ffma2_rn(xvs, xvs, __fmul2_rn(rv, rv));
+          const float2 rhs = __fmul2_rn(vv, gap);
+#pragma unroll
           for (int q = 0; q < 2; q++) {
             const int b = q ? bj : bi;
             const unsigned cb = q ? cb1 : cb0;
@@ -871,54 +915,20 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
             const bool want_coll = d < 3 || (am & 0x00ffffffu) == 0x00ffffffu;
             const bool active = has && kin && k != b && (q == 0 || !is_cell);
             const bool doit = active && (is_cell ? want_cell : want_coll);
-            bool keep = doit;
+            const bool plain = (((q ? bm1 : bm0) >> k) & 1ull) == 0ull; // no bond bookkeeping
+            const bool far_apart = (q ? gap.y : gap.x) > far_min;
+            const bool receding = (q ? rv.y : rv.x) > (q ? rv_min.y : rv_min.x);
+            const bool misses = (q ? lhs.y : lhs.x) < (q ? rhs.y : rhs.x);
+            const bool reject = d >= 3 && plain && far_apart && (receding || misses);
 #ifdef HMC_VERIFY_PREFILTER
-            bool flagged = false;
-#endif
-            { // (two_pass implies short_chain: the one-image wrap below needs |d/l| < 1.5)
-              const bool plain = (((q ? bm1 : bm0) >> k) & 1ull) == 0ull; // no bond bookkeeping
-              // separation at the partner's clock: subtract in double (unwrapped coordinates
-              // may be large), then everything else in single precision
-              float dx = float(k0.x - (q ? J.x : I.x));
-              float dy = float(k0.y - (q ? J.y : I.y));
-              float dz = float(k1.x - (q ? J.z : I.z));
-              const float ux = float(q ? J.vx : I.vx), uy = float(q ? J.vy : I.vy),
-                          uz = float(q ? J.vz : I.vz);
-              // magnitudes that bound every intermediate: X for lengths, V for speeds
-              const float X = fabsf(dx) + fabsf(dy) + fabsf(dz) + Wd;
-              const float V = W + fabsf(ux) + fabsf(uy) + fabsf(uz);
-              dx = fmaf(wx, dtf, dx);
-              dy = fmaf(wy, dtf, dy);
-              dz = fmaf(wz, dtf, dz);
-              // (a predicted pair sits in adjacent cells: |separation| <= 2 lcell <= 0.4 boxes
-              // per axis with ncell >= 5, far from the half-box where the image would flip)
-              const float tx = dx * finv_l, ty_ = dy * finv_l, tz = dz * finv_l;
-              dx -= copysignf(fabsf(tx) >= 0.5f ? fl : 0.0f, tx);
-              dy -= copysignf(fabsf(ty_) >= 0.5f ? fl : 0.0f, ty_);
-              dz -= copysignf(fabsf(tz) >= 0.5f ? fl : 0.0f, tz);
-              const float ex = wx - ux, ey = wy - uy, ez = wz - uz;
-              const float rv = fmaf(dx, ex, fmaf(dy, ey, dz * ez));
-              const float vv = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
-              const float gap = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, -frh2)));
-              // error bounds with unit roundoff u = 6e-8: |d rv| <= 10 u X V,
-              // |d rr| <= 13 u X^2, |d (rv^2 - vv gap)| <= 42 u X^2 V^2; the margins below
-              // are 16-40 times larger
-              const float XV = X * V;
-              const bool far_apart = gap > 1e-5f * X * X;
-              const bool receding = rv > 1e-5f * XV;
-              const bool misses = fmaf(rv, rv, -vv * gap) < -1e-4f * XV * XV;
-              const bool reject = d >= 3 && plain && far_apart && (receding || misses);
-#ifdef HMC_VERIFY_PREFILTER
-              flagged = doit && reject; // predict it anyway; pass 2 checks it has no event
+            const bool keep = doit;
+            const bool flagged = doit && reject; // predicted anyway; pass 2 checks it has no event
 #else
-              keep = doit && !reject;
+            const bool keep = doit && !reject;
 #endif
-            }
-            // collision: every slot of bi / bj that is not (re)predicted is cleared
-            if (active && !is_cell && !keep) {
-              s.evt[slot] = CUDART_INF;
-              s.evty[slot] = 0xffu;
-            }
+            // collision: every slot of bi / bj that is not (re)predicted is cleared (its
+            // latched type is only ever read for a slot that wins the argmin)
+            if (active && !is_cell && !keep) s.evt[slot] = CUDART_INF;
             const unsigned gbits = (__ballot_sync(0xffffffffu, keep) >> gshift) & gmask;
 #ifdef HMC_VERIFY_PREFILTER
             if (keep) s.plist[cnt + __popc(gbits & below)] = uint8_t((k + q * nb) | (flagged ? 0x80 : 0));
