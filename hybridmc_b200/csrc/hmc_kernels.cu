@@ -72,9 +72,9 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const uint16_t *slot_
   Smem s;
   double *d = reinterpret_cast<double *>(base);
   s.b = d;
-  s.evt = d + BSTRIDE * nb;
-  s.evty = reinterpret_cast<uint8_t *>(d + BSTRIDE * nb + nslots);
-  s.plist = s.evty + nslots;
+  s.evt = d + BSTRIDE * nb; // [nslots] + one scratch slot that absorbs predicated-off stores
+  s.evty = reinterpret_cast<uint8_t *>(d + BSTRIDE * nb + nslots + 1);
+  s.plist = s.evty + nslots + 1; // evty: [nslots] + scratch; plist: [2 nb] + scratch
   s.slot_row = slot_row;
   s.nb = nb;
   return s;
@@ -928,12 +928,14 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
 #endif
             // collision: every slot of bi / bj that is not (re)predicted is cleared (its
             // latched type is only ever read for a slot that wins the argmin)
-            if (active && !is_cell && !keep) s.evt[slot] = CUDART_INF;
+            // (branch-free: a store that is not wanted goes to the scratch slot)
+            s.evt[(active && !is_cell && !keep) ? slot : a.nslots] = CUDART_INF;
             const unsigned gbits = (__ballot_sync(0xffffffffu, keep) >> gshift) & gmask;
+            const int dst = keep ? cnt + __popc(gbits & below) : 2 * nb;
 #ifdef HMC_VERIFY_PREFILTER
-            if (keep) s.plist[cnt + __popc(gbits & below)] = uint8_t((k + q * nb) | (flagged ? 0x80 : 0));
+            s.plist[dst] = uint8_t((k + q * nb) | (flagged ? 0x80 : 0));
 #else
-            if (keep) s.plist[cnt + __popc(gbits & below)] = uint8_t(k + q * nb);
+            s.plist[dst] = uint8_t(k + q * nb);
 #endif
             cnt += __popc(gbits);
           }
@@ -965,10 +967,9 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
           const double tnew = have ? tt : CUDART_INF;
           // collision: overwrite (or clear) the slot; crossing: keep the earlier of old/new
           const bool store = on && (is_cell ? (have && tnew < s.evt[slot]) : true);
-          if (store) {
-            s.evt[slot] = tnew;
-            s.evty[slot] = uint8_t(pty);
-          }
+          const int wslot = store ? slot : a.nslots; // scratch slot when nothing is to be written
+          s.evt[wslot] = tnew;
+          s.evty[wslot] = uint8_t(pty);
         }
       }
       __syncwarp();
@@ -1445,7 +1446,7 @@ template <int G> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hm
 size_t hmc_smem_per_replica(int nb) {
   const size_t npairs = size_t(nb) * (nb - 1) / 2;
   const size_t nslots = nb + npairs;
-  size_t bytes = 8 * (size_t(BSTRIDE) * nb + nslots) + nslots + 2 * size_t(nb);
+  size_t bytes = 8 * (size_t(BSTRIDE) * nb + nslots + 1) + (nslots + 1) + 2 * size_t(nb) + 1;
   return (bytes + 15) & ~size_t(15);
 }
 
