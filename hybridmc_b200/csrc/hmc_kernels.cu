@@ -601,7 +601,9 @@ __device__ __forceinline__ void table_argmin(const Smem &s, int nslots, int lane
                                              int &bs) {
   bt = CUDART_INF;
   bs = 0x7fffffff;
-  for (int q = lane; q < nslots; q += G) {
+  // group-uniform trip count (the tail lanes re-read the last slot: same time, same index)
+  for (int base = 0; base < nslots; base += G) {
+    const int q = min(base + lane, nslots - 1);
     const double t = s.evt[q];
     const bool lt = t < bt;
     bt = lt ? t : bt;
@@ -611,7 +613,7 @@ __device__ __forceinline__ void table_argmin(const Smem &s, int nslots, int lane
   for (int off = G / 2; off > 0; off >>= 1) {
     const double ot = __shfl_xor_sync(0xffffffffu, bt, off);
     const int os = __shfl_xor_sync(0xffffffffu, bs, off);
-    const bool take = ot < bt || (ot == bt && os < bs);
+    const bool take = (ot < bt) | ((ot == bt) & (os < bs)); // (no short-circuit branches)
     bt = take ? ot : bt;
     bs = take ? os : bs;
   }
@@ -646,9 +648,13 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
     // BeadCellEvent (hardspheres.cc:1622-1645): new cell from the wall latched at
     // prediction (t_until_cell :589-666)
     if (is_cell) {
-      cxn = wall == 0 ? (cxn + 1) % nc : wall == 1 ? (cxn - 1 + nc) % nc : cxn;
-      cyn = wall == 2 ? (cyn + 1) % nc : wall == 3 ? (cyn - 1 + nc) % nc : cyn;
-      czn = wall == 4 ? (czn + 1) % nc : wall == 5 ? (czn - 1 + nc) % nc : czn;
+      // (c +- 1) mod nc by compare/select: an integer '%' is a ~20-instruction sequence
+      const int step = (wall & 1u) ? -1 : 1;
+      int moved = (wall < 2 ? cxn : wall < 4 ? cyn : czn) + step;
+      moved = moved < 0 ? nc - 1 : (moved >= nc ? 0 : moved);
+      cxn = wall < 2 ? moved : cxn;
+      cyn = (wall >= 2 && wall < 4) ? moved : cyn;
+      czn = (wall >= 4 && wall < 6) ? moved : czn;
     }
     // update_pos (:1040-1047) for both beads (the same bead twice for a crossing)
     const double dti = t - I.t, dtj = t - J.t;
@@ -956,7 +962,8 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
           const int b = second ? bj : bi;
           const int k = on ? (second ? idx - nb : idx) : b;
           const int d = abs(b - k);
-          const int slot = k == b ? nb : int(s.slot_row[min(b, k)]) + max(b, k);
+          const int srow = int(s.slot_row[min(b, k)]) + max(b, k);
+          const int slot = k == b ? nb : srow; // an in-range dummy for an idle lane
           double tt;
           const unsigned pty =
               predict_pair(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), on, tt);
@@ -966,7 +973,8 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
 #endif
           const double tnew = have ? tt : CUDART_INF;
           // collision: overwrite (or clear) the slot; crossing: keep the earlier of old/new
-          const bool store = on && (is_cell ? (have && tnew < s.evt[slot]) : true);
+          const double told = s.evt[slot];
+          const bool store = on & (!is_cell | (have & (tnew < told)));
           const int wslot = store ? slot : a.nslots; // scratch slot when nothing is to be written
           s.evt[wslot] = tnew;
           s.evty[wslot] = uint8_t(pty);
