@@ -152,12 +152,25 @@ __device__ __forceinline__ double mindist_pair(const KArgs &a, double d) {
   if (a.short_chain) return d - copysign(fabs(t) >= 0.5 ? a.l : 0.0, t);
   return d - round_away(t) * a.l;
 }
+// the same with the (launch-uniform) choice made at compile time: the event path calls it
+// three times per prediction
+template <bool SC> __device__ __forceinline__ double mindist_pair_t(const KArgs &a, double d) {
+  const double t = d * a.inv_l;
+  if (SC) return d - copysign(fabs(t) >= 0.5 ? a.l : 0.0, t);
+  return d - round_away(t) * a.l;
+}
 
 // Box::mindist, box.h:22-26
 __device__ __forceinline__ void mindist3(const KArgs &a, double &dx, double &dy, double &dz) {
   dx = mindist_pair(a, dx);
   dy = mindist_pair(a, dy);
   dz = mindist_pair(a, dz);
+}
+template <bool SC>
+__device__ __forceinline__ void mindist3_t(const KArgs &a, double &dx, double &dy, double &dz) {
+  dx = mindist_pair_t<SC>(a, dx);
+  dy = mindist_pair_t<SC>(a, dy);
+  dz = mindist_pair_t<SC>(a, dz);
 }
 
 struct Bead {
@@ -178,6 +191,29 @@ __device__ __forceinline__ Bead load_bead(const Smem &s, int k) {
   return b;
 }
 
+// x y z vx vy vz t of one bead record as three 128-bit + one 64-bit store, all under one
+// predicate (st.shared with a guard predicate instead of a branch around the stores)
+__device__ __forceinline__ void store_bead(double *rec, const Bead &b, double t, bool p) {
+  const unsigned addr = unsigned(__cvta_generic_to_shared(rec));
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t"
+      "@p st.shared.v2.f64 [%1], {%2, %3};\n\t"
+      "@p st.shared.v2.f64 [%1+16], {%4, %5};\n\t"
+      "@p st.shared.v2.f64 [%1+32], {%6, %7};\n\t"
+      "@p st.shared.f64 [%1+48], %8;\n\t}"
+      :
+      : "r"(int(p)), "r"(addr), "d"(b.x), "d"(b.y), "d"(b.z), "d"(b.vx), "d"(b.vy), "d"(b.vz),
+        "d"(t)
+      : "memory");
+}
+__device__ __forceinline__ void sts_pred_u32(unsigned *ptr, unsigned v, bool p) {
+  const unsigned addr = unsigned(__cvta_generic_to_shared(ptr));
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p st.shared.u32 [%1], %2;\n\t}"
+               :
+               : "r"(int(p)), "r"(addr), "r"(v)
+               : "memory");
+}
+
 // delta_tpv (hardspheres.cc:372-392) followed by the type logic of if_nearest_bond /
 // if_nnearest_bond (:863-923) or if_coll (:425-476).  Returns the latched event type,
 // or 0xff when the reference queues nothing.
@@ -193,6 +229,7 @@ __device__ __forceinline__ Bead load_bead(const Smem &s, int k) {
 // Beads are passed as indices (p, q) with p_is_lo telling which one is lower: the
 // reference starts from (i,j) = (lo,hi) and swaps iff times[lo] < times[hi], so "i" is
 // the bead with the later clock and, on a tie, the lower index.
+template <bool SC>
 __device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, const Smem &s,
                                                  int p, int q, bool p_is_lo, int d,
                                                  unsigned info, bool want, double &tout) {
@@ -212,7 +249,7 @@ __device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, c
   double dx = xj + vxj * dt - xi;
   double dy = yj + vyj * dt - yi;
   double dz = zj + vzj * dt - zi;
-  mindist3(a, dx, dy, dz);
+  mindist3_t<SC>(a, dx, dy, dz);
   const double dvx = vxj - vxi, dvy = vyj - vyi, dvz = vzj - vzi;
   const double rv = dx * dvx + dy * dvy + dz * dvz;
   const double vv = dvx * dvx + dvy * dvy + dvz * dvz;
@@ -495,7 +532,7 @@ __device__ __forceinline__ unsigned check_constraints(const KArgs &a, const Rep 
 
 // initialize_system, main.cc:45-95: constraint checks, init_cells, velocities
 // (+ COM shift), and the full prediction fill of the event table.
-template <int G>
+template <int G, bool SC>
 // Executed by the whole warp; only groups with `on` change their state (the others are in
 // the middle of a step).
 __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *normals,
@@ -583,7 +620,7 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
       doit = mine && (adj_mask(BCELL(s, i), BCELL(s, j), unsigned(a.ncell - 1) * 0x00010101u) &
                       0x00ffffffu) == 0x00ffffffu;
     double tt;
-    const unsigned ty = predict_pair(a, R, s, i, j, true, d, __ldg(&R.pinfo[p]), doit && on, tt);
+    const unsigned ty = predict_pair<SC>(a, R, s, i, j, true, d, __ldg(&R.pinfo[p]), doit && on, tt);
     if (mine && on) {
       s.evt[nb + p] = (ty != 0xffu) ? tt : CUDART_INF;
       s.evty[nb + p] = uint8_t(ty);
@@ -625,7 +662,7 @@ __device__ __forceinline__ void table_argmin(const Smem &s, int nslots, int lane
 // The body is one instruction path for collisions and cell crossings alike (selects
 // instead of branches): the replica groups that share a warp execute it together, and
 // a crossing simply discards the collision arithmetic it did not need.
-template <int G>
+template <int G, bool SC>
 __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s, bool has,
                                            double bt, int bs, int lane) {
   const int nb = a.nb, nc = a.ncell;
@@ -666,7 +703,7 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
     J.z += J.vz * dtj;
     // collision events, hardspheres.cc:1106-1620: final_vel (:1050-1061)
     double dx = J.x - I.x, dy = J.y - I.y, dz = J.z - I.z;
-    mindist3(a, dx, dy, dz);
+    mindist3_t<SC>(a, dx, dy, dz);
     const unsigned info = is_cell ? 0u : unsigned(__ldg(&R.pinfo[pidx]));
     const unsigned tb = info & 0x7fu;
     const bool perm = (info & 0x80u) != 0;
@@ -717,26 +754,12 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
     R.n_cell += (has && is_cell) ? 1u : 0u;
     R.n_coll += (has && !is_cell) ? 1u : 0u;
     __syncwarp();
-    if (!has) {
-      // nothing to write
-    } else if (lane == 0) {
-      BX(s, bi) = I.x;
-      BY(s, bi) = I.y;
-      BZ(s, bi) = I.z;
-      BVX(s, bi) = I.vx;
-      BVY(s, bi) = I.vy;
-      BVZ(s, bi) = I.vz;
-      BT(s, bi) = t;
-      BCELL(s, bi) = unsigned(cxn) | (unsigned(cyn) << 8) | (unsigned(czn) << 16);
-    } else if (lane == 1 && !is_cell) {
-      BX(s, bj) = J.x;
-      BY(s, bj) = J.y;
-      BZ(s, bj) = J.z;
-      BVX(s, bj) = J.vx;
-      BVY(s, bj) = J.vy;
-      BVZ(s, bj) = J.vz;
-      BT(s, bj) = t;
-    }
+    // write the 1-2 event beads back: lane 0 stores bead bi (and its cell), lane 1 bead bj,
+    // as predicated 128-bit stores (no divergent branch in the lockstep path)
+    store_bead(s.b + BSTRIDE * bi, I, t, has && lane == 0);
+    sts_pred_u32(reinterpret_cast<unsigned *>(s.b + BSTRIDE * bi + F_CELL),
+                 unsigned(cxn) | (unsigned(cyn) << 8) | (unsigned(czn) << 16), has && lane == 0);
+    store_bead(s.b + BSTRIDE * bj, J, t, has && lane == 1 && !is_cell);
     if (has) trace_event(a, R, lane, is_cell ? unsigned(HMC_EV_BEAD_CELL) : ty, bi, is_cell ? wall : bj, t);
     __syncwarp();
 
@@ -755,9 +778,11 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
       const int b = qb ? bj : bi;
       const double *rec = s.b + BSTRIDE * b;
       const int axc = on ? ax : 0;
-      const double v = on ? rec[F_VX + axc] : 1.0;
-      const double pp = on ? rec[F_X + axc] : 0.0;
-      const double cc = on ? double((BCELL(s, b) >> (8 * axc)) & 0xffu) : 0.0;
+      const double v_ld = rec[F_VX + axc], p_ld = rec[F_X + axc]; // (unconditional loads)
+      const unsigned c_ld = BCELL(s, b);
+      const double v = on ? v_ld : 1.0;
+      const double pp = on ? p_ld : 0.0;
+      const double cc = on ? double((c_ld >> (8 * axc)) & 0xffu) : 0.0;
       const double dd = mindist1(a, a.lcell * cc - pp);
       const double numer = v > 0 ? dd + a.lcell : dd;
       const double cand = numer / v;
@@ -781,10 +806,13 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
         dtc = t2 ? c2 : dtc;
         w = t2 ? 4u + unsigned(v2 >> 1) : w;
         cr = cr || t2;
-        if (has && lane == 0 && q < nbead) {
+        {
           const int bq = q ? bj : bi;
-          s.evt[bq] = cr ? BT(s, bq) + dtc : CUDART_INF;
-          s.evty[bq] = uint8_t(w);
+          const double tb_ = BT(s, bq);
+          // (scratch slot unless this lane owns the store)
+          const int wq = (has && lane == 0 && q < nbead) ? bq : a.nslots;
+          s.evt[wq] = cr ? tb_ + dtc : CUDART_INF;
+          s.evty[wq] = uint8_t(w);
         }
       }
     }
@@ -796,7 +824,8 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
       const unsigned ncm1x3 = unsigned(nc - 1) * 0x00010101u;
       // the cell coordinate that became adjacent through a crossing
       int far = int((cb0 >> (8 * axis)) & 0xffu) + ((wall & 1u) ? -1 : 1);
-      far = far < 0 ? far + nc : (far >= nc ? far - nc : far);
+      far += far < 0 ? nc : 0;
+      far -= far >= nc ? nc : 0;
       const unsigned others = 0x00ffffffu & ~(0xffu << (8 * axis)); // the two other axes
       if (!a.two_pass) {
         // short chains: a single pass over all 2 nb candidates (the pre-filter below costs
@@ -824,7 +853,7 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
           const bool doit = active && (is_cell ? want_cell : want_coll);
           double tt;
           const unsigned pty =
-              predict_pair(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), doit, tt);
+              predict_pair<SC>(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), doit, tt);
           const bool have = doit && pty != 0xffu;
           const double tnew = have ? tt : CUDART_INF;
           // collision: overwrite (or clear) the slot; crossing: keep the earlier of old/new
@@ -966,7 +995,7 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
           const int slot = k == b ? nb : srow; // an in-range dummy for an idle lane
           double tt;
           const unsigned pty =
-              predict_pair(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), on, tt);
+              predict_pair<SC>(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), on, tt);
           const bool have = on && pty != 0xffu;
 #ifdef HMC_VERIFY_PREFILTER
           if (have && (raw & 0x80)) R.err |= 0x40000000u; // the pre-filter rejected a real event
@@ -1219,7 +1248,7 @@ __device__ __forceinline__ double wl_gamma(const KArgs &a, unsigned iter_wl) {
   return iter_wl == 0 ? a.gamma0 : 1.0 / double(iter_wl); // main.cc:283,302-303
 }
 
-template <int G> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hmc_ensemble_kernel(const __grid_constant__ KArgs a) {
+template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hmc_ensemble_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & (G - 1);
   const unsigned gmask = group_mask<G>();
@@ -1348,7 +1377,7 @@ template <int G> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hm
             const double *nrm =
                 (a.normals && do_init) ? a.normals + (size_t(r) * nunits + ninit) * size_t(nb) * 3
                                        : nullptr;
-            init_step<G>(a, R, s, nrm, a.md_draw_base + ninit, lane, gmask, do_init);
+            init_step<G, SC>(a, R, s, nrm, a.md_draw_base + ninit, lane, gmask, do_init);
             const double h0 = hamiltonian(a, R, s);
             if (do_init) {
               e0 = h0;
@@ -1416,7 +1445,7 @@ template <int G> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hm
           if (!warp_any<G>(in_step || e < E)) break;
           continue;
         }
-        event_body<G>(a, R, s, has, bt, bs, lane);
+        event_body<G, SC>(a, R, s, has, bt, bs, lane);
       }
     }
 
@@ -1468,7 +1497,7 @@ int hmc_pick_group(int nb) {
   return 32;
 }
 
-template <int G>
+template <int G, bool SC>
 static cudaError_t launch_g(const KArgs &a, cudaStream_t stream, int *grid_out, int *block_out) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -1481,14 +1510,14 @@ static cudaError_t launch_g(const KArgs &a, cudaStream_t stream, int *grid_out, 
   for (int cand = HMC_BLOCK; cand >= 64 && cand >= G; cand /= 2) {
     const size_t sm = size_t(cand / G) * a.smem_per_replica +
                       ((size_t(a.nb) * sizeof(uint16_t) + 15) & ~size_t(15));
-    cudaError_t e = cudaFuncSetAttribute(hmc_ensemble_kernel<G>,
+    cudaError_t e = cudaFuncSetAttribute(hmc_ensemble_kernel<G, SC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));
     if (e != cudaSuccess) {
       cudaGetLastError();
       continue;
     }
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, hmc_ensemble_kernel<G>, cand, sm);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, hmc_ensemble_kernel<G, SC>, cand, sm);
     if (e != cudaSuccess) {
       cudaGetLastError();
       continue;
@@ -1501,7 +1530,7 @@ static cudaError_t launch_g(const KArgs &a, cudaStream_t stream, int *grid_out, 
     }
   }
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(hmc_ensemble_kernel<G>,
+  cudaError_t e = cudaFuncSetAttribute(hmc_ensemble_kernel<G, SC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   const int groups_per_cta = block / G;
@@ -1510,7 +1539,7 @@ static cudaError_t launch_g(const KArgs &a, cudaStream_t stream, int *grid_out, 
   long long grid = (long long)sms * per_sm;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  hmc_ensemble_kernel<G><<<int(grid), block, smem, stream>>>(a);
+  hmc_ensemble_kernel<G, SC><<<int(grid), block, smem, stream>>>(a);
   if (grid_out) *grid_out = int(grid);
   if (block_out) *block_out = block;
   return cudaGetLastError();
@@ -1518,9 +1547,17 @@ static cudaError_t launch_g(const KArgs &a, cudaStream_t stream, int *grid_out, 
 
 cudaError_t hmc_launch(const KArgs &a, int group, cudaStream_t stream, int *grid_out,
                        int *block_out) {
+  // SC: min-image fast path for chains shorter than 1.5 boxes, chosen per launch
+  if (a.short_chain) {
+    switch (group) {
+    case 8: return launch_g<8, true>(a, stream, grid_out, block_out);
+    case 16: return launch_g<16, true>(a, stream, grid_out, block_out);
+    default: return launch_g<32, true>(a, stream, grid_out, block_out);
+    }
+  }
   switch (group) {
-  case 8: return launch_g<8>(a, stream, grid_out, block_out);
-  case 16: return launch_g<16>(a, stream, grid_out, block_out);
-  default: return launch_g<32>(a, stream, grid_out, block_out);
+  case 8: return launch_g<8, false>(a, stream, grid_out, block_out);
+  case 16: return launch_g<16, false>(a, stream, grid_out, block_out);
+  default: return launch_g<32, false>(a, stream, grid_out, block_out);
   }
 }

@@ -180,3 +180,24 @@ def test_maximum_chain_length():
     d = load_config("50bead_9bond")
     d.update(nbeads=64, transient_bonds=[[1, 9]], permanent_bonds=[], length=48.0, ncell=10)
     _trace_pair(params_from_json(d), 2, phase=PHASE_EQ)
+
+
+def test_long_chain_general_min_image():
+    """20 beads stretched (19 x 1.17 = 22.2) are longer than 1.45 boxes of length 12: the
+    engine must take the general min-image path (and, with ncell = 4, the single-pass
+    partner loop) and still match the oracle bit for bit."""
+    d = load_config("test")
+    d.update(length=12.0, ncell=4)
+    from hybridmc_b200.params import transition_jsons
+    p = params_from_json(transition_jsons(d)[0][3])
+    assert (p.nbeads - 1) * p.near_max >= 1.45 * p.length
+    _run_eq_trace(p, 4, 60000)
+
+
+@pytest.mark.parametrize("name,two_pass", [("8bead_1bond", "1"), ("test", "0"), ("test", "1")])
+def test_partner_loop_variants_agree_with_oracle(name, two_pass, monkeypatch):
+    """the pre-filtered two-pass partner loop and the single-pass loop are interchangeable:
+    both forced on chains where the heuristic would pick the other"""
+    monkeypatch.setenv("HMC_TWO_PASS", two_pass)
+    p = transition_params(name, 0) if name != "8bead_1bond" else params_from_json(load_config(name))
+    _run_eq_trace(p, 4, 60000)
