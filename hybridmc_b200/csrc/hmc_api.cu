@@ -189,6 +189,18 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.short_chain = (double(h->nb - 1) * p.near_max < 1.45 * p.length) ? 1 : 0;
   a.chain_max = double(h->nb - 1) * p.near_max;
   {
+    const float fl = float(p.length), finv = float(1.0 / p.length), frh2 = float(p.rh * p.rh);
+    a.pf_invl2 = make_float2(finv, finv);
+    a.pf_nl2 = make_float2(-fl, -fl);
+    a.pf_nrh2 = make_float2(-frh2, -frh2);
+    a.pf_magic = make_float2(12582912.0f, 12582912.0f); // 1.5 * 2^23: rint by adding
+    a.pf_nmagic = make_float2(-12582912.0f, -12582912.0f);
+    a.pf_c1e5 = make_float2(1e-5f, 1e-5f);
+    a.pf_c1e2 = make_float2(1e-2f, 1e-2f);
+    a.pf_xc = float(a.chain_max) + fl;
+    a.pf_l = fl;
+  }
+  {
     const char *tp = getenv("HMC_TWO_PASS"); // experiment switch: 0 / 1 overrides the heuristic
     // needs: one-image wrap (short chain) and partners in adjacent cells closer than half a
     // box in every axis (ncell >= 5), so that single precision picks the same image

@@ -91,6 +91,10 @@ struct KArgs {
   uint32_t max_events_per_step;
   int short_chain; // (nb-1)*near_max < 1.45*length: bead-bead differences stay below 1.5 boxes
   double chain_max; // (nb-1)*near_max: the fully stretched chain
+  // packed single-precision constants of the partner pre-filter (read as 64-bit
+  // constant-bank operands, so they occupy no registers)
+  float2 pf_invl2, pf_nl2, pf_nrh2, pf_magic, pf_nmagic, pf_c1e5, pf_c1e2;
+  float pf_xc, pf_l;
   int two_pass;    // partner re-prediction as pre-filter + compacted exact pass (chains >= 16 beads)
 };
 

@@ -109,6 +109,8 @@ struct Rep {
 
 // "does any replica group of this warp satisfy p" for a GROUP-UNIFORM predicate: with one
 // group per warp (G == 32) that is p itself and no vote instruction is needed.
+__device__ __forceinline__ float2 f2(float x) { return make_float2(x, x); }
+
 template <int G> __device__ __forceinline__ bool warp_any(bool p) {
   if constexpr (G == 32) {
     return p;
@@ -878,21 +880,16 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
         // The two tests of a lane (partner k against bi and against bj) are the same
         // arithmetic on two data sets: they run as packed float2 operations (FFMA2 / FADD2
         // / FMUL2 of sm_100), bi in .x and bj in .y.
-        const float fl = float(a.l);
-        const float2 invl2 = make_float2(float(a.inv_l), float(a.inv_l));
-        const float2 nl2 = make_float2(-fl, -fl);
-        const float2 nrh2 = make_float2(-float(a.rh2), -float(a.rh2));
-        const float2 magic = make_float2(12582912.0f, 12582912.0f); // 1.5 * 2^23: rint by adding
-        const float2 nmagic = make_float2(-12582912.0f, -12582912.0f);
         // event-bead velocities (negated) and their 1-norms
         const float2 nux = make_float2(-float(I.vx), -float(J.vx));
         const float2 nuy = make_float2(-float(I.vy), -float(J.vy));
         const float2 nuz = make_float2(-float(I.vz), -float(J.vz));
         const float2 U = make_float2(fabsf(nux.x) + fabsf(nuy.x) + fabsf(nuz.x),
                                      fabsf(nux.y) + fabsf(nuy.y) + fabsf(nuz.y));
+        const float2 nox = make_float2(0.0f, -float(J.x - I.x)), noy = make_float2(0.0f, -float(J.y - I.y)),
+                     noz = make_float2(0.0f, -float(J.z - I.z));
         // lengths: |x_k(t_k) - x_b(t)| <= stretched chain + |v_k| dt; one more |v_k| dt for the
         // advance and one box for the wrap
-        const float Xc = float(a.chain_max) + fl;
         const unsigned gshift = (threadIdx.x & 31u) & ~unsigned(G - 1);
         const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
         const unsigned below = (1u << lane) - 1u;
@@ -909,31 +906,33 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
           const float wx = float(k1.y), wy = float(k2.x), wz = float(k2.y);
           const float W = fabsf(wx) + fabsf(wy) + fabsf(wz);
           // magnitudes that bound every intermediate: X for lengths, V for speeds
-          const float X = fmaf(W + W, dtf, Xc);
+          const float X = fmaf(W + W, dtf, a.pf_xc);
           const float2 XV = __fmul2_rn(make_float2(X, X), __fadd2_rn(make_float2(W, W), U));
           const float far_min = 1e-5f * X * X;
           // separation at the partner's clock: subtract in double (unwrapped coordinates
           // may be large), then everything else in single precision
           const float2 dt2 = make_float2(dtf, dtf);
           const float2 wx2 = make_float2(wx, wx), wy2 = make_float2(wy, wy), wz2 = make_float2(wz, wz);
-          float2 dx = __ffma2_rn(wx2, dt2, make_float2(float(k0.x - I.x), float(k0.x - J.x)));
-          float2 dy = __ffma2_rn(wy2, dt2, make_float2(float(k0.y - I.y), float(k0.y - J.y)));
-          float2 dz = __ffma2_rn(wz2, dt2, make_float2(float(k1.x - I.z), float(k1.x - J.z)));
+          // (x_k - x_j = (x_k - x_i) - (x_j - x_i): one conversion per axis, the offset of
+          // bead bj from bead bi is event-uniform and already in single precision)
+          float2 dx = __ffma2_rn(wx2, dt2, __fadd2_rn(f2(float(k0.x - I.x)), nox));
+          float2 dy = __ffma2_rn(wy2, dt2, __fadd2_rn(f2(float(k0.y - I.y)), noy));
+          float2 dz = __ffma2_rn(wz2, dt2, __fadd2_rn(f2(float(k1.x - I.z)), noz));
           // minimum image, d - l rint(d/l).  (A predicted pair sits in adjacent cells:
           // |separation| <= 2 lcell <= 0.4 boxes per axis with ncell >= 5, far from the
           // half-box where the rounding mode or a single-precision error could matter.)
-          dx = __ffma2_rn(__fadd2_rn(__ffma2_rn(dx, invl2, magic), nmagic), nl2, dx);
-          dy = __ffma2_rn(__fadd2_rn(__ffma2_rn(dy, invl2, magic), nmagic), nl2, dy);
-          dz = __ffma2_rn(__fadd2_rn(__ffma2_rn(dz, invl2, magic), nmagic), nl2, dz);
+          dx = __ffma2_rn(__fadd2_rn(__ffma2_rn(dx, a.pf_invl2, a.pf_magic), a.pf_nmagic), a.pf_nl2, dx);
+          dy = __ffma2_rn(__fadd2_rn(__ffma2_rn(dy, a.pf_invl2, a.pf_magic), a.pf_nmagic), a.pf_nl2, dy);
+          dz = __ffma2_rn(__fadd2_rn(__ffma2_rn(dz, a.pf_invl2, a.pf_magic), a.pf_nmagic), a.pf_nl2, dz);
           const float2 ex = __fadd2_rn(wx2, nux), ey = __fadd2_rn(wy2, nuy), ez = __fadd2_rn(wz2, nuz);
           const float2 rv = __ffma2_rn(dx, ex, __ffma2_rn(dy, ey, __fmul2_rn(dz, ez)));
           const float2 vv = __ffma2_rn(ex, ex, __ffma2_rn(ey, ey, __fmul2_rn(ez, ez)));
-          const float2 gap = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, nrh2)));
-          // error bounds with unit roundoff u = 6e-8: |d rv| <= 10 u X V, |d rr| <= 13 u X^2,
-          // |d (rv^2 - vv gap)| <= 42 u X^2 V^2; the margins are 16-40 times larger:
+          const float2 gap = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, a.pf_nrh2)));
+          // error bounds with unit roundoff u = 6e-8: |d rv| <= 12 u X V, |d rr| <= 17 u X^2,
+          // |d (rv^2 - vv gap)| <= 50 u X^2 V^2; the margins are 14-33 times larger:
           // receding: rv > 1e-5 XV;  misses: rv^2 + 1e-4 (XV)^2 < vv gap
-          const float2 rv_min = __fmul2_rn(XV, make_float2(1e-5f, 1e-5f));
-          const float2 xvs = __fmul2_rn(XV, make_float2(1e-2f, 1e-2f));
+          const float2 rv_min = __fmul2_rn(XV, a.pf_c1e5);
+          const float2 xvs = __fmul2_rn(XV, a.pf_c1e2);
           const float2 lhs = __ffma2_rn(xvs, xvs, __fmul2_rn(rv, rv));
           const float2 rhs = __fmul2_rn(vv, gap);
 #pragma unroll
