@@ -788,35 +788,24 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
       const double dd = mindist1(a, a.lcell * cc - pp);
       const double numer = v > 0 ? dd + a.lcell : dd;
       const double cand = numer / v;
-      const int code = (on && v != 0.0 ? 1 : 0) | (v < 0 ? 2 : 0); // bit0 valid, bit1 negative wall
+      // earliest wall of each bead: fold z into y, then that into x, inside the lane
+      // triplets (strict '<': on a tie the earlier axis stays, as the reference's x,y,z
+      // scan does); an axis at rest competes with +inf
+      double ct = (on && v != 0.0) ? cand : CUDART_INF;
+      int cw = 2 * axc + (v < 0 ? 1 : 0); // wall code: 2 axis + (negative side)
 #pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const double c0 = __shfl_sync(0xffffffffu, cand, 3 * q + 0, G);
-        const double c1 = __shfl_sync(0xffffffffu, cand, 3 * q + 1, G);
-        const double c2 = __shfl_sync(0xffffffffu, cand, 3 * q + 2, G);
-        const int v0 = __shfl_sync(0xffffffffu, code, 3 * q + 0, G);
-        const int v1 = __shfl_sync(0xffffffffu, code, 3 * q + 1, G);
-        const int v2 = __shfl_sync(0xffffffffu, code, 3 * q + 2, G);
-        bool cr = (v0 & 1) != 0;
-        double dtc = cr ? c0 : 0.0;
-        unsigned w = unsigned(v0 >> 1);
-        const bool t1 = (v1 & 1) && (!cr || c1 < dtc);
-        dtc = t1 ? c1 : dtc;
-        w = t1 ? 2u + unsigned(v1 >> 1) : w;
-        cr = cr || t1;
-        const bool t2 = (v2 & 1) && (!cr || c2 < dtc);
-        dtc = t2 ? c2 : dtc;
-        w = t2 ? 4u + unsigned(v2 >> 1) : w;
-        cr = cr || t2;
-        {
-          const int bq = q ? bj : bi;
-          const double tb_ = BT(s, bq);
-          // (scratch slot unless this lane owns the store)
-          const int wq = (has && lane == 0 && q < nbead) ? bq : a.nslots;
-          s.evt[wq] = cr ? tb_ + dtc : CUDART_INF;
-          s.evty[wq] = uint8_t(w);
-        }
+      for (int pass = 1; pass >= 0; pass--) {
+        const double ot = __shfl_down_sync(0xffffffffu, ct, 1, G);
+        const int ow = __shfl_down_sync(0xffffffffu, cw, 1, G);
+        const bool take = (ax == pass) & on & (ot < ct);
+        ct = take ? ot : ct;
+        cw = take ? ow : cw;
       }
+      // lane 0 now holds bead bi's wall, lane 3 bead bj's (scratch slot for everyone else)
+      const bool mine = has && (lane == 0 || (lane == 3 && !is_cell));
+      const int wq = mine ? b : a.nslots;
+      s.evt[wq] = BT(s, b) + ct;
+      s.evty[wq] = uint8_t(cw);
     }
 
     // partner predictions, both beads in one flattened lane loop
