@@ -640,9 +640,22 @@ __device__ __forceinline__ void table_argmin(const Smem &s, int nslots, int lane
                                              int &bs) {
   bt = CUDART_INF;
   bs = 0x7fffffff;
-  // group-uniform trip count (the tail lanes re-read the last slot: same time, same index)
-  for (int base = 0; base < nslots; base += G) {
-    const int q = min(base + lane, nslots - 1);
+  // group-uniform trip counts: full strides first (pointer + immediate offsets once
+  // unrolled), then one clamped stride whose tail lanes re-read the last slot (same time,
+  // same index)
+  const double *col = s.evt + lane;
+  int q = lane;
+  const int nfull = nslots - G;
+#pragma unroll 4
+  for (int base = 0; base <= nfull; base += G) {
+    const double t = col[base];
+    const bool lt = t < bt;
+    bt = lt ? t : bt;
+    bs = lt ? q : bs;
+    q += G;
+  }
+  {
+    q = min(q, nslots - 1);
     const double t = s.evt[q];
     const bool lt = t < bt;
     bt = lt ? t : bt;
