@@ -209,6 +209,9 @@ def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # NCCL writes its version / debug lines to stdout by default: keep stdout for the one
+    # JSON line of the contract
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local)
