@@ -955,7 +955,10 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
             const bool far_apart = (q ? gap.y : gap.x) > far_min;
             const bool receding = (q ? rv.y : rv.x) > (q ? rv_min.y : rv_min.x);
             const bool misses = (q ? lhs.y : lhs.x) < (q ? rhs.y : rhs.x);
-            const bool reject = d >= 3 && plain && far_apart && (receding || misses);
+            // (dtf < 0: the partner's clock is ahead of this event — only reachable after a
+            // bond has left its well, a state the reference aborts on at the next step; such
+            // pairs go to the exact path like everything else that is unusual)
+            const bool reject = d >= 3 && plain && far_apart && (receding || misses) && dtf >= 0.0f;
 #ifdef HMC_VERIFY_PREFILTER
             const bool keep = doit;
             const bool flagged = doit && reject; // predicted anyway; pass 2 checks it has no event
@@ -999,7 +1002,33 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
               predict_pair<SC>(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), on, tt);
           const bool have = on && pty != 0xffu;
 #ifdef HMC_VERIFY_PREFILTER
-          if (have && (raw & 0x80)) R.err |= 0x40000000u; // the pre-filter rejected a real event
+          // the pre-filter rejected a real event: flag it and record the first offender
+          // (bits 8-13 b, 14-19 k, 20 crossing) for profiles/verify_prefilter.py
+          if (have && (raw & 0x80) && !(R.err & 0x40000000u)) {
+            R.err |= 0x40000000u | (unsigned(b) << 8) | (unsigned(k) << 14) | (is_cell ? 1u << 20 : 0u);
+            if (R.tracing && R.live) { // dump the pair's state as records of type >= 200
+              unsigned n = *a.trace_n;
+              auto put = [&](unsigned ty, double v) {
+                if (n < a.trace_cap) {
+                  hmc_event e;
+                  e.t = v;
+                  e.type = ty;
+                  e.i = unsigned(b);
+                  e.j = unsigned(k);
+                  e.pad = 0;
+                  a.trace[n] = e;
+                }
+                n++;
+              };
+              put(200, t); put(201, BT(s, b)); put(202, BT(s, k)); put(203, tt); put(204, double(pty));
+              put(205, BX(s, b)); put(206, BY(s, b)); put(207, BZ(s, b));
+              put(208, BVX(s, b)); put(209, BVY(s, b)); put(210, BVZ(s, b)); put(211, double(BCELL(s, b)));
+              put(212, BX(s, k)); put(213, BY(s, k)); put(214, BZ(s, k));
+              put(215, BVX(s, k)); put(216, BVY(s, k)); put(217, BVZ(s, k)); put(218, double(BCELL(s, k)));
+              put(219, double(is_cell ? int(wall) : -1));
+              *a.trace_n = n;
+            }
+          }
 #endif
           const double tnew = have ? tt : CUDART_INF;
           // collision: overwrite (or clear) the slot; crossing: keep the earlier of old/new
