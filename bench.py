@@ -209,9 +209,12 @@ def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    # NCCL writes its version / debug lines to stdout by default: keep stdout for the one
-    # JSON line of the contract
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # NCCL (and anything else in the process) may write to stdout — its version banner does
+    # even with NCCL_DEBUG_FILE set: park the real stdout and point fd 1 at stderr until the
+    # one JSON line of the contract is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local)
@@ -371,7 +374,10 @@ def run_gpu_arm(args):
             v, kind, sample = cpu_events_per_sec(args.config, args.cpu_seconds, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": sample}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     e.close()
     if world > 1:
         dist.destroy_process_group()
