@@ -82,7 +82,7 @@ def fpt_from_fit(x_knot, y, inner, order=24):
             b = qx[i * order + j]
             xx = 0.5 * (b - a) * t + 0.5 * (b + a)
             ss = _basis(x_knot, xx) @ y
-            cdf[i * order + j] = left[i] + (0.5 * (b - a) * w * np.exp(-(ss - s.min())) / z).sum()
+            cdf[i * order + j] = left[i] + (0.5 * (b - a) * w * np.exp(np.clip(-(ss - s.min()), -745.0, 700.0)) / z).sum()
     integrand = cdf * cdf / pdf if inner else (1.0 - cdf) * (1.0 - cdf) / pdf
     return float((qw * integrand).sum())
 
