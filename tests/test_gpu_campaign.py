@@ -54,3 +54,34 @@ def test_two_layers_of_test_json(tmp_path):
                                max_layers=2, hist_bins=2048, wl=False, eq_iters=2,
                                log=lambda *a: None)
     assert summary2 == []
+
+
+def test_staircase_sweep_layer0(tmp_path):
+    """init_json.py --bp/--rc (tools/init_json.py:93-120): the transition that forms the
+    staircase bond runs in stages rc = 3.0 -> 2.2 -> 1.5, each stage started from the previous
+    stage's bonded structure, intermediate files carry their rc in the name"""
+    master = load_config("test")
+    bonds = sorted(sorted(b) for b in master["nonlocal_bonds"])
+    bp = bonds[0]
+    out = str(tmp_path / "stair")
+    summary, _ = run_campaign(master, out, replicas=48, iters_per_round=2, max_rounds=2,
+                              max_layers=1, hist_bins=512, wl=False, eq_iters=2,
+                              log=lambda *a: None, stair_bp=bp, stair_rc=[3.0, 2.2, 1.5])
+    names = sorted(f[:-3] for f in os.listdir(out) if f.endswith(".h5"))
+    stair = [n for n in names if n.startswith("hybridmc_0_000_100")]
+    assert stair == ["hybridmc_0_000_100", "hybridmc_0_000_100_2.2", "hybridmc_0_000_100_3.0"]
+    assert len(names) == 3 + 2 and len(summary) == 5
+    import json
+    for n, rc, st in (("hybridmc_0_000_100_3.0", 3.0, None), ("hybridmc_0_000_100_2.2", 2.2, 3.0),
+                      ("hybridmc_0_000_100", 1.5, 2.2)):
+        with open(os.path.join(out, n + ".json")) as f:
+            d = json.load(f)
+        assert d["rc"] == rc and d.get("stair") == st and "p_rc" not in d
+        assert (d.get("stair_bonds") == [bp]) == (st is not None)
+        with File(os.path.join(out, n + ".h5")) as f:
+            assert np.isfinite(f["s_bias"]).all() and len(f["unique_config"]["pos"]) == 1
+            # the structure handed on has the bond inside this stage's rc
+            pos = f["unique_config"]["pos"][0]
+            dd = pos[bp[1]] - pos[bp[0]]
+            dd -= master["length"] * np.round(dd / master["length"])
+            assert np.linalg.norm(dd) < rc
