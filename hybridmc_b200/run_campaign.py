@@ -27,6 +27,11 @@ import time
 
 import numpy as np
 
+if __package__ in (None, ""):  # started by path, the way tools/run.py starts init_json.py
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import hybridmc_b200  # noqa: F401
+    __package__ = "hybridmc_b200"
+
 from .campaign import layers_of, run_transition_ensemble, shard
 from .engine import init_pos_chain
 from .output import File, write_hdf5
