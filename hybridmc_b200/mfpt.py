@@ -127,3 +127,78 @@ def transition_fpts(hist, rmax, params, bond_column=None):
     inner = fpt_from_hist(h[1], rmax, params.rh, params.rc, True)
     outer = fpt_from_hist(h[0], rmax, params.rc, None, False)
     return inner, outer
+
+
+# ---- the reference tool's command line (tools/mfpt.py:32-150) -----------------------------
+
+def fpt_rows(data, dist=None, hist=None, rmax=None, nboot=0, seed=0):
+    """Rows of the reference's per-transition csv: for every nonlocal bond i that is not
+    permanent, [i, fpt_on, fpt_off (, var_on, var_off)] — for the transient bond fpt_on is
+    the INNER time of the formed bond and fpt_off the outer time of the open bond; for any
+    other bond both are outer times, with the transient bond formed / open
+    (tools/mfpt.py:99-146).  Input: the `dist` samples [rows][n_nonlocal] of the executable,
+    or the engine's state-split histograms `hist[n_nonlocal][2][nbins]` over [0, rmax)."""
+    rc, rh = data["rc"], data["rh"]
+    nl = [sorted(b) for b in data["nonlocal_bonds"]]
+    t_ind = nl.index(sorted(data["transient_bonds"][0]))
+    p_ind = [i for i, b in enumerate(nl) if b in [sorted(p) for p in data.get("permanent_bonds", [])]]
+    rng = np.random.default_rng(seed)
+    rows = []
+    for i in range(len(nl)):
+        if i in p_ind:
+            continue
+        if dist is not None:
+            d_i, d_t = np.asarray(dist)[:, i], np.asarray(dist)[:, t_ind]
+            if i == t_ind:
+                on, off = d_i[d_i < rc], d_i[d_i >= rc]
+            else:
+                on, off = d_i[(d_t < rc) & (d_i >= rc)], d_i[(d_t >= rc) & (d_i >= rc)]
+
+            def est(x, inner):
+                return fpt_from_samples(x, rh, rc, True) if inner else \
+                    fpt_from_samples(x, rc, x.max(), False)
+
+            def var(x, inner):  # bootstrap over half-size resamples (tools/mfpt.py:383-395)
+                vals = [est(rng.choice(x, size=len(x) // 2, replace=True), inner) for _ in range(nboot)]
+                return float(np.var(vals, ddof=1))
+            row = [i, est(on, i == t_ind), est(off, False)]
+            if nboot > 1:
+                row += [var(on, i == t_ind), var(off, False)]
+        else:
+            h = np.asarray(hist)[i]
+            row = [i, fpt_from_hist(h[1], rmax, rh, rc, True) if i == t_ind else
+                   fpt_from_hist(h[1], rmax, rc, None, False),
+                   fpt_from_hist(h[0], rmax, rc, None, False)]
+        rows.append(row)
+    return rows
+
+
+def main(argv=None):
+    """python -m hybridmc_b200.mfpt json hdf5 nboot csv — the arguments of tools/mfpt.py"""
+    import argparse
+    import csv
+    import json
+
+    from .output import File
+    ap = argparse.ArgumentParser()
+    ap.add_argument("json", help="json input file")
+    ap.add_argument("hdf5", help="hdf5 input file (executable output: dist samples; campaign "
+                                 "output: dist_hist histograms)")
+    ap.add_argument("nboot", type=int, help="number of bootstrap samples to run (samples only)")
+    ap.add_argument("csv", help="csv output file")
+    ap.add_argument("--layers", help="accepted for compatibility")
+    args = ap.parse_args(argv)
+    with open(args.json) as f:
+        data = json.load(f)
+    with File(args.hdf5) as f:
+        if "dist" in f.keys() and len(f["dist"]):
+            print("number of distances =", len(f["dist"]))
+            rows = fpt_rows(data, dist=f["dist"], nboot=args.nboot)
+        else:
+            rows = fpt_rows(data, hist=f["dist_hist"], rmax=float(f.attrs["dist_hist_rmax"]))
+    with open(args.csv, "w", newline="") as f:
+        csv.writer(f).writerows(rows)
+
+
+if __name__ == "__main__":
+    main()

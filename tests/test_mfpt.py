@@ -59,3 +59,33 @@ def test_samples_and_histogram_agree_on_simulated_distances(oracle):
     outer_h = mfpt.fpt_from_hist(h_off, rmax, p.rc, None, False)
     assert abs(inner_h / inner_s - 1) < 0.05 and abs(outer_h / outer_s - 1) < 0.05
     assert 0.005 < inner_s < 0.05 and 0.5 < outer_s < 50  # same order as mfpt.csv short loops
+
+
+def test_command_line_matches_the_reference_tools_layout(tmp_path):
+    """python -m hybridmc_b200.mfpt json hdf5 nboot csv (tools/mfpt.py:32-150) on an output
+    file with `dist` samples: one row per non-permanent bond, transient bond -> inner/outer,
+    other bonds -> outer with the transient bond formed / open"""
+    import csv
+    import json
+
+    from hybridmc_b200 import mfpt, output
+    rng = np.random.default_rng(3)
+    rc, rh = 1.5, 1.25
+    n = 6000
+    formed = rng.random(n) < 0.4
+    d_t = np.where(formed, rng.uniform(rh, rc, n), rc + rng.gamma(2.0, 0.8, n))
+    d_o = rc + rng.gamma(2.0, 1.0, n) + 0.3 * formed
+    d_p = rng.uniform(rh, rc, n)
+    data = dict(rc=rc, rh=rh, nonlocal_bonds=[[2, 6], [6, 10], [10, 14]],
+                transient_bonds=[[6, 10]], permanent_bonds=[[10, 14]])
+    (tmp_path / "t.json").write_text(json.dumps(data))
+    output.write_hdf5(str(tmp_path / "t.h5"), {"dist": np.stack([d_o, d_t, d_p], axis=1)})
+    mfpt.main([str(tmp_path / "t.json"), str(tmp_path / "t.h5"), "0", str(tmp_path / "t.csv")])
+    rows = [[float(x) for x in r] for r in csv.reader(open(tmp_path / "t.csv"))]
+    assert [int(r[0]) for r in rows] == [0, 1]  # the permanent bond (index 2) has no row
+    inner = mfpt.fpt_from_samples(d_t[d_t < rc], rh, rc, True)
+    outer = mfpt.fpt_from_samples(d_t[d_t >= rc], rc, d_t.max(), False)
+    assert rows[1][1] == pytest.approx(inner, rel=1e-9) and rows[1][2] == pytest.approx(outer, rel=1e-9)
+    on = d_o[(d_t < rc) & (d_o >= rc)]
+    assert rows[0][1] == pytest.approx(mfpt.fpt_from_samples(on, rc, on.max(), False), rel=1e-9)
+    assert all(np.isfinite(r[1]) and r[1] > 0 and r[2] > 0 for r in rows)
