@@ -834,6 +834,15 @@ int hmc_get_dist_hist(hmc_handle h, uint64_t *hist) {
   return sync(h);
 }
 
+int hmc_dist_hist_device_ptr(hmc_handle h, void **dptr, uint64_t *n_u64) {
+  if (!h || !dptr || !n_u64) return fail(h, "hmc_dist_hist_device_ptr: null");
+  if (!h->hist_bins) return fail(h, "hmc_dist_hist_device_ptr: histogram not enabled");
+  const size_t stride = h->n_nonlocal_max ? h->n_nonlocal_max : 1;
+  *dptr = h->d_hist;
+  *n_u64 = uint64_t(h->T) * stride * 2 * h->hist_bins;
+  return 0;
+}
+
 int hmc_get_unique_config(hmc_handle h, double *pos, double *vel, uint8_t *found) {
   if (!h) return fail(h, "null handle");
   const size_t n = size_t(h->R) * h->nb * 3;

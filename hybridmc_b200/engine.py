@@ -37,6 +37,7 @@ EXPORTS = [
     "hmc_get_moves_done", "hmc_init_pos_engine", "hmc_run_program_exact",
     "hmc_run_program_exact_sink", "hmc_get_schedule_state", "hmc_set_schedule_state",
     "hmc_set_s_bias_per_replica",
+    "hmc_dist_hist_device_ptr",
     "hmc_h5_create", "hmc_h5_dataset", "hmc_h5_attribute", "hmc_h5_write", "hmc_h5_destroy",
 ]
 
@@ -264,6 +265,12 @@ class Engine:
         out = np.zeros((self.T, max(self.n_nonlocal, 1), 2, self._hist_bins), dtype=np.uint64)
         self._ck(self.lib.hmc_get_dist_hist(self.h, _p(out)))
         return out
+
+    def dist_hist_device_ptr(self):
+        """(device address, length in u64) of the histogram block, for an in-place all-reduce"""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.hmc_dist_hist_device_ptr(self.h, C.byref(ptr), C.byref(n)))
+        return ptr.value, int(n.value)
 
     def get_unique_config(self):
         pos = np.zeros((self.R, self.nb, 3))

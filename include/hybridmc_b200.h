@@ -221,6 +221,10 @@ int hmc_get_config_int(hmc_handle h, uint64_t *config_int, uint32_t *n);
  * hist[n_transitions][n_nonlocal][2][nbins] over [0, rmax), one count per MD step. */
 int hmc_enable_dist_hist(hmc_handle h, unsigned nbins, double rmax);
 int hmc_get_dist_hist(hmc_handle h, uint64_t *hist);
+/* Device pointer of that u64 histogram block (the first-passage-time accumulators) for an
+ * in-place NCCL all-reduce when one transition's replicas are spread over several GPUs;
+ * *n_u64 = n_transitions * n_nonlocal * 2 * nbins.  Fails if histograms are not enabled. */
+int hmc_dist_hist_device_ptr(hmc_handle h, void **dptr, uint64_t *n_u64);
 /* First recorded configuration with config == 1 per replica
  * (unique_config/{pos,vel}, main.cc:211-216): pos/vel[R_total][nbeads][3],
  * found[R_total]. */

@@ -119,3 +119,39 @@ def test_ensemble_snapshot_resume_is_bit_identical():
         e2.run(PHASE_MAIN, 2, 2)
         assert np.array_equal(e2.get_positions().view(np.uint64), ref_pos.view(np.uint64))
         assert np.array_equal(e2.get_config(), ref_cfg)
+
+
+def test_accumulator_device_views_for_the_all_reduce():
+    """the two u64 blocks a multi-GPU run all-reduces in place (per-state counts and the
+    first-passage-time histograms) seen through their device pointers equal the host copies,
+    and an in-place doubling (what an all-reduce over two identical ranks does) is what the
+    getters then return"""
+    import torch
+
+    class View:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False),
+                                             "version": 2}
+    p = transition_params("test", 0)
+    with _ensemble(p, 64) as e:
+        e.enable_dist_hist(128, 16.0)
+        e.run(PHASE_MAIN, 0, 2)
+        e.sync()
+        hist = e.get_dist_hist()
+        counts = e.get_counts()[0]
+        assert hist.sum() > 0 and counts.sum() > 0
+        hptr, hn = e.dist_hist_device_ptr()
+        cptr, cn = e.counts_device_ptr()
+        assert hn == hist.size
+        ht = torch.as_tensor(View(hptr, hn), device="cuda")
+        ct = torch.as_tensor(View(cptr, cn), device="cuda")
+        assert np.array_equal(ht.cpu().numpy().astype(np.uint64).reshape(hist.shape), hist)
+        assert np.array_equal(ct.cpu().numpy()[:counts.size].astype(np.uint64).reshape(counts.shape), counts)
+        ht.mul_(2)
+        ct.mul_(2)
+        torch.cuda.synchronize()
+        assert np.array_equal(e.get_dist_hist(), 2 * hist)
+        assert np.array_equal(e.get_counts()[0], 2 * counts)
+    with _ensemble(p, 8) as e:
+        with pytest.raises(Exception, match="histogram not enabled"):
+            e.dist_hist_device_ptr()
