@@ -128,3 +128,17 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp")):
                 txt = open(os.path.join(base, f)).read()
                 assert "oracle_lib" not in txt and "libhmc_oracle" not in txt and "libhmc_ref" not in txt, f
+
+
+def test_stair_stages_follow_init_json():
+    """tools/init_json.py:93-120: stage j runs with rc = rc[j], the previous radius as
+    `stair` wall on the transient bond, p_rc only above layer 0, rc in every name but the last"""
+    from hybridmc_b200.run_campaign import stair_stages
+    d = dict(rc=1.5, transient_bonds=[[4, 16]], permanent_bonds=[])
+    st = stair_stages(d, 0, 1.5, [3.0, 2.2, 1.5])
+    assert [s for _, s in st] == ["_3.0", "_2.2", ""]
+    assert [x["rc"] for x, _ in st] == [3.0, 2.2, 1.5]
+    assert "stair" not in st[0][0] and st[1][0]["stair"] == 3.0 and st[2][0]["stair"] == 2.2
+    assert st[1][0]["stair_bonds"] == [[4, 16]] and all("p_rc" not in x for x, _ in st)
+    st1 = stair_stages(dict(d, permanent_bonds=[[2, 6]]), 1, 1.5, [3.0, 1.5])
+    assert all(x["p_rc"] == 1.5 for x, _ in st1) and d["rc"] == 1.5 and "stair" not in d
