@@ -202,3 +202,111 @@ def test_writer_errors(tmp_path):
     assert lib.hmc_h5_dataset(h, b"x", 9, 1, dims, buf, 16) < 0
     lib.hmc_h5_destroy.argtypes = [C.c_void_p]
     lib.hmc_h5_destroy(h)
+
+
+def _chunked_file(datasets):
+    """A minimal HDF5 file assembled by hand from the format specification, with the layout
+    the stock reference executable uses for its extensible datasets (src/writer.h): dataspace
+    with an unlimited first dimension, layout v3 CHUNKED, version-1 chunk B-tree, optional
+    deflate filter.  datasets: {name: (array, chunk_rows, deflate)}; flat names only."""
+    import zlib
+    buf = bytearray(96)  # superblock, patched at the end
+    UNDEF = 0xFFFFFFFFFFFFFFFF
+
+    def align():
+        buf.extend(b"\0" * (-len(buf) % 8))
+
+    def msg(mtype, body, flags=0):
+        body = body + b"\0" * (-len(body) % 8)
+        return struct.pack("<HHBBH", mtype, len(body), flags, 0, 0) + body
+
+    headers = {}
+    for name, (arr, crows, deflate) in datasets.items():
+        rank = arr.ndim
+        cshape = (crows,) + arr.shape[1:]
+        # chunks: partial edge chunks are stored at full size
+        keys = []
+        for r0 in range(0, arr.shape[0], crows):
+            chunk = np.zeros(cshape, dtype=arr.dtype)
+            part = arr[r0:r0 + crows]
+            chunk[:len(part)] = part
+            raw = chunk.tobytes()
+            if deflate:
+                raw = zlib.compress(raw, 6)
+            align()
+            keys.append((len(raw), 0, (r0,) + (0,) * (rank - 1) + (0,), len(buf)))
+            buf.extend(raw)
+        align()
+        btree = len(buf)
+        node = b"TREE" + struct.pack("<BBHQQ", 1, 0, len(keys), UNDEF, UNDEF)
+        for size, mask, offs, addr in keys:
+            node += struct.pack("<II", size, mask) + struct.pack("<%dQ" % (rank + 1), *offs)
+            node += struct.pack("<Q", addr)
+        node += struct.pack("<II", 0, 0) + struct.pack("<%dQ" % (rank + 1), arr.shape[0], *([0] * rank))
+        buf.extend(node)
+        space = struct.pack("<BBBBI", 1, rank, 1, 0, 0) + struct.pack("<%dQ" % rank, *arr.shape) + \
+            struct.pack("<%dQ" % rank, UNDEF, *arr.shape[1:])
+        if arr.dtype == np.float64:
+            dtype = bytes.fromhex("11203f000800000000004000340b0034ff030000")
+        else:
+            dtype = struct.pack("<BBBBIHH", 0x10, 0, 0, 0, arr.itemsize, 0, 8 * arr.itemsize)
+        msgs = msg(0x0001, space) + msg(0x0003, dtype, 1) + msg(0x0005, bytes([2, 3, 2, 1, 0, 0, 0, 0]), 1)
+        n = 4
+        if deflate:
+            msgs += msg(0x000B, struct.pack("<BB6x", 1, 1) + struct.pack("<HHHH", 1, 8, 1, 1) +
+                        b"deflate\0" + struct.pack("<II", 6, 0))
+            n += 1
+        msgs += msg(0x0008, struct.pack("<BBBQ", 3, 2, rank + 1, btree) +
+                    struct.pack("<%dI" % (rank + 1), *cshape, arr.itemsize))
+        align()
+        headers[name] = len(buf)
+        buf.extend(struct.pack("<BBHII4x", 1, 0, n, 1, len(msgs)) + msgs)
+    # root group: heap, one symbol node, B-tree, object header
+    names = sorted(headers)
+    heap_data = bytearray(8)
+    offs = []
+    for nm in names:
+        offs.append(len(heap_data))
+        heap_data.extend(nm.encode() + b"\0")
+        heap_data.extend(b"\0" * (-len(heap_data) % 8))
+    free = len(heap_data)
+    heap_data.extend(struct.pack("<QQ", 1, 16))
+    align()
+    heap = len(buf)
+    buf.extend(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), free, heap + 32) + heap_data)
+    align()
+    snod = len(buf)
+    node = b"SNOD" + struct.pack("<BBH", 1, 0, len(names))
+    for nm, off in zip(names, offs):
+        node += struct.pack("<QQII16x", off, headers[nm], 0, 0)
+    buf.extend(node + b"\0" * (328 - len(node)))
+    btree = len(buf)
+    node = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, UNDEF, UNDEF) + struct.pack("<QQQ", 0, snod, offs[-1])
+    buf.extend(node + b"\0" * (544 - len(node)))
+    root = len(buf)
+    m = msg(0x0011, struct.pack("<QQ", btree, heap))
+    buf.extend(struct.pack("<BBHII4x", 1, 0, 1, 1, len(m)) + m)
+    sb = SIG + bytes([0, 0, 0, 0, 0, 8, 8, 0]) + struct.pack("<HHI", 4, 16, 0) + \
+        struct.pack("<QQQQ", 0, UNDEF, len(buf), UNDEF) + struct.pack("<QQII", 0, root, 1, 0) + \
+        struct.pack("<QQ", btree, heap)
+    assert len(sb) == 96
+    buf[:96] = sb
+    return bytes(buf)
+
+
+SIG = h5lite.SIGNATURE
+
+
+def test_reads_chunked_deflated_datasets_like_the_stock_executable_writes(tmp_path):
+    """(format per specification; NOT pinned against libhdf5 — no chunked file exists here)"""
+    rng = np.random.default_rng(5)
+    dist = rng.random((23, 4))           # chunk (10, 4): two full chunks + a partial one
+    cfg = rng.integers(0, 4, 2500).astype(np.uint64)  # chunk 1024, unfiltered
+    path = tmp_path / "stock_like.h5"
+    path.write_bytes(_chunked_file({"dist": (dist, 10, True), "cfg": (cfg, 1024, False)}))
+    ds, attrs = h5lite.read(str(path))
+    assert attrs == {} and sorted(ds) == ["cfg", "dist"]
+    assert ds["dist"].dtype == np.float64 and np.array_equal(ds["dist"], dist)
+    assert ds["cfg"].dtype == np.uint64 and np.array_equal(ds["cfg"], cfg)
+    with output.File(str(path)) as f:
+        assert np.array_equal(f["dist"][:], dist)
