@@ -70,8 +70,9 @@ def build_executable(force=False):
     if not force and os.path.exists(EXE) and all(
             os.path.getmtime(d) <= os.path.getmtime(EXE) for d in deps if os.path.exists(d)):
         return EXE
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", EXE, src, LIB, "-Wl,-rpath,$ORIGIN",
-           "-l:libstdc++.so.6"]
+    # zlib: --input-file may be a stock reference output (chunked + deflate datasets)
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-DH5LITE_WITH_ZLIB", "-o", EXE, src, LIB,
+           "-Wl,-rpath,$ORIGIN", "-l:libstdc++.so.6", "-lz"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

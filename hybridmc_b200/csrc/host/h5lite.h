@@ -30,6 +30,9 @@
 #include <string>
 #include <unistd.h>
 #include <vector>
+#ifdef H5LITE_WITH_ZLIB
+#include <zlib.h>
+#endif
 
 namespace h5lite {
 
@@ -349,6 +352,7 @@ class Reader {
 public:
   std::map<std::string, Item> datasets; // full paths "group/name"
   std::map<std::string, Item> attrs;    // root attributes
+  std::vector<std::string> skipped;     // items that could not be decoded, with the reason
 
   bool open(const std::string &path) {
     FILE *fp = std::fopen(path.c_str(), "rb");
@@ -374,6 +378,7 @@ public:
     d_ = &s;
     datasets.clear();
     attrs.clear();
+    skipped.clear();
     try {
       // the superblock sits at 0, 512, 1024, ... (user block)
       size_t sb = 0;
@@ -500,10 +505,117 @@ private:
       const size_t at = lver == 3 ? layout->at + 4 : layout->at + 8 + 4 * u8(layout->at + 1) + 4;
       need(at, nbytes);
       fill(it, d_->data() + at, nbytes);
+    } else if (cls == 2 && lver == 3) {
+      read_chunked(it, msgs, *layout, nbytes, path);
     } else {
-      throw std::runtime_error("h5lite: chunked dataset " + path + " not supported");
+      throw std::runtime_error("h5lite: layout of dataset " + path + " not supported");
     }
     datasets[path] = it;
+  }
+
+  // layout v3 class 2 (what the stock reference executable writes, src/writer.h): rank+1,
+  // chunk B-tree address, chunk dims (last = element size); deflate needs zlib
+  // (-DH5LITE_WITH_ZLIB).  Per the specification; not pinned against a libhdf5 file.
+  struct Chunk {
+    std::vector<uint64_t> offs;
+    uint32_t size, mask;
+    uint64_t addr;
+  };
+  void walk_chunks(uint64_t node, unsigned rank1, std::vector<Chunk> &out) const {
+    need(node, 24);
+    if (std::memcmp(d_->data() + node, "TREE", 4) != 0 || u8(node + 4) != 1)
+      throw std::runtime_error("h5lite: bad chunk B-tree node");
+    const uint8_t level = u8(node + 5);
+    const unsigned used = u16(node + 6);
+    const size_t ksize = 8 + 8 * rank1;
+    size_t p = node + 24;
+    for (unsigned k = 0; k < used; k++, p += ksize + 8) {
+      const uint64_t child = base_ + u64(p + ksize);
+      if (level) {
+        walk_chunks(child, rank1, out);
+        continue;
+      }
+      Chunk c;
+      c.size = u32(p);
+      c.mask = u32(p + 4);
+      for (unsigned a = 0; a + 1 < rank1; a++) c.offs.push_back(u64(p + 8 + 8 * a));
+      c.addr = child;
+      out.push_back(c);
+    }
+  }
+  void read_chunked(Item &it, const std::vector<Msg> &msgs, const Msg &layout, size_t nbytes,
+                    const std::string &path) const {
+    if (it.dtype == VSTR) throw std::runtime_error("h5lite: chunked strings not supported");
+    const unsigned rank1 = u8(layout.at + 2), rank = rank1 - 1;
+    const uint64_t btree = u64(layout.at + 3);
+    std::vector<uint64_t> cdim(rank);
+    for (unsigned a = 0; a < rank; a++) cdim[a] = u32(layout.at + 11 + 4 * a);
+    const size_t esize = type_size(it.dtype);
+    if (rank != it.dims.size() || rank == 0 || u32(layout.at + 11 + 4 * rank) != esize)
+      throw std::runtime_error("h5lite: inconsistent chunked layout of " + path);
+    // filter pipeline (message 0x000b, v1/v2): only deflate (1) is undone here
+    std::vector<uint16_t> filters;
+    for (const Msg &m : msgs) {
+      if (m.type != 0x000b) continue;
+      const uint8_t ver = u8(m.at), n = u8(m.at + 1);
+      size_t p = m.at + (ver == 1 ? 8 : 2);
+      for (unsigned f = 0; f < n; f++) {
+        const uint16_t id = u16(p);
+        size_t nlen = 0;
+        if (ver == 1 || id >= 256) { nlen = u16(p + 2); p += 4; } else p += 2;
+        const uint16_t ncd = u16(p + 2);
+        p += 4 + (ver == 1 ? detail::pad8(nlen) : nlen) + 4 * size_t(ncd);
+        if (ver == 1 && (ncd & 1)) p += 4;
+        filters.push_back(id);
+      }
+    }
+    it.bytes.assign(nbytes, '\0');
+    if (!nbytes || btree == detail::UNDEF) return;
+    std::vector<Chunk> chunks;
+    walk_chunks(base_ + btree, rank1, chunks);
+    size_t cbytes = esize;
+    for (uint64_t c : cdim) cbytes *= size_t(c);
+    std::string raw;
+    for (const Chunk &c : chunks) {
+      need(c.addr, c.size);
+      const char *src = d_->data() + c.addr;
+      for (size_t f = filters.size(); f-- > 0;) {
+        if (c.mask & (1u << f)) continue;
+        if (filters[f] != 1) throw std::runtime_error("h5lite: only the deflate filter is supported");
+#ifdef H5LITE_WITH_ZLIB
+        raw.assign(cbytes, '\0');
+        uLongf n = uLongf(cbytes);
+        if (uncompress(reinterpret_cast<Bytef *>(&raw[0]), &n, reinterpret_cast<const Bytef *>(src),
+                       c.size) != Z_OK || n != cbytes)
+          throw std::runtime_error("h5lite: cannot inflate a chunk of " + path);
+        src = raw.data();
+#else
+        throw std::runtime_error("h5lite: built without zlib, cannot read deflated dataset " + path);
+#endif
+      }
+      // copy the part of the chunk that lies inside the dataset, row by row of the last axis
+      std::vector<uint64_t> idx(rank, 0), lim(rank);
+      bool empty = false;
+      for (unsigned a = 0; a < rank; a++) {
+        if (c.offs[a] >= it.dims[a]) { empty = true; break; }
+        lim[a] = std::min<uint64_t>(cdim[a], it.dims[a] - c.offs[a]);
+      }
+      if (empty) continue;
+      for (;;) {
+        size_t in = 0, out = 0;
+        for (unsigned a = 0; a < rank; a++) {
+          in = in * size_t(cdim[a]) + size_t(idx[a]);
+          out = out * size_t(it.dims[a]) + size_t(c.offs[a] + idx[a]);
+        }
+        std::memcpy(&it.bytes[out * esize], src + in * esize, size_t(lim[rank - 1]) * esize);
+        int a = int(rank) - 2;
+        for (; a >= 0; a--) {
+          if (++idx[a] < lim[a]) break;
+          idx[a] = 0;
+        }
+        if (a < 0) break;
+      }
+    }
   }
 
   void read_attr(const Msg &m) {
@@ -555,13 +667,25 @@ private:
     const Msg *stab = nullptr;
     for (const Msg &m : msgs)
       if (m.type == 0x0011) stab = &m;
+    // an item this reader cannot decode (another datatype, a newer message version, ...)
+    // is skipped and listed, it does not make the rest of the file unreadable
     if (!stab) {
-      read_dataset(header, msgs, path);
+      try {
+        read_dataset(header, msgs, path);
+      } catch (const std::runtime_error &e) {
+        skipped.push_back(path + ": " + e.what());
+      }
       return;
     }
     if (is_root)
       for (const Msg &m : msgs)
-        if (m.type == 0x000c) read_attr(m);
+        if (m.type == 0x000c) {
+          try {
+            read_attr(m);
+          } catch (const std::runtime_error &e) {
+            skipped.push_back(std::string("attribute: ") + e.what());
+          }
+        }
     const uint64_t btree = base_ + u64(stab->at), heap = base_ + u64(stab->at + 8);
     need(heap, 32);
     if (std::memcmp(d_->data() + heap, "HEAP", 4) != 0) throw std::runtime_error("h5lite: bad local heap");

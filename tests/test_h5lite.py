@@ -27,8 +27,8 @@ def fnv1a(raw):
 @pytest.fixture(scope="module")
 def dump_tool(tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("h5") / "h5dump")
-    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-o", exe,
-                    os.path.join(HERE, "h5lite_dump.cpp"), "-l:libstdc++.so.6"], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-DH5LITE_WITH_ZLIB", "-o", exe,
+                    os.path.join(HERE, "h5lite_dump.cpp"), "-l:libstdc++.so.6", "-lz"], check=True)
 
     def run(path):
         r = subprocess.run([exe, path], capture_output=True, text=True)
@@ -297,7 +297,7 @@ def _chunked_file(datasets):
 SIG = h5lite.SIGNATURE
 
 
-def test_reads_chunked_deflated_datasets_like_the_stock_executable_writes(tmp_path):
+def test_reads_chunked_deflated_datasets_like_the_stock_executable_writes(tmp_path, dump_tool):
     """(format per specification; NOT pinned against libhdf5 — no chunked file exists here)"""
     rng = np.random.default_rng(5)
     dist = rng.random((23, 4))           # chunk (10, 4): two full chunks + a partial one
@@ -310,3 +310,12 @@ def test_reads_chunked_deflated_datasets_like_the_stock_executable_writes(tmp_pa
     assert ds["cfg"].dtype == np.uint64 and np.array_equal(ds["cfg"], cfg)
     with output.File(str(path)) as f:
         assert np.array_equal(f["dist"][:], dist)
+    # the C++ reader the executable uses for --input-file
+    got = dump_tool(str(path))
+    assert got[("dataset", "dist")] == (0, dist.shape, dist.nbytes, fnv1a(dist.tobytes()))
+    assert got[("dataset", "cfg")] == (2, cfg.shape, cfg.nbytes, fnv1a(cfg.tobytes()))
+    pos = rng.random((3, 5, 3))  # unique_config/pos-like: 3-D, chunk (2, 5, 3), deflate
+    p3 = tmp_path / "pos.h5"
+    p3.write_bytes(_chunked_file({"pos": (pos, 2, True)}))
+    assert np.array_equal(h5lite.read(str(p3))[0]["pos"], pos)
+    assert dump_tool(str(p3))[("dataset", "pos")] == (0, pos.shape, pos.nbytes, fnv1a(pos.tobytes()))
