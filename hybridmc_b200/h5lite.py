@@ -271,13 +271,13 @@ class _Parser:
     def walk(self, header, path, datasets, attrs):
         msgs = self.messages(header)
         stab = [m for m in msgs if m[0] == 0x0011]
-        if not stab:
-            datasets[path] = self.dataset(msgs, path)
-            return
         for mtype, _f, body, _s in msgs:
             if mtype == 0x000C:
                 name, val = self.attribute(body)
                 attrs.setdefault(path, {})[name] = val
+        if not stab:
+            datasets[path] = self.dataset(msgs, path)
+            return
         body = stab[0][2]
         btree, heap = self.base + self.q(body), self.base + self.q(body + 8)
         if self.d[heap:heap + 4] != b"HEAP":
@@ -312,6 +312,16 @@ def read(path):
     datasets, attrs = {}, {}
     p.walk(p.root_header, "", datasets, attrs)
     return datasets, attrs.get("", {})
+
+
+def read_attrs(path):
+    """-> {object path ("" = root): {attribute name: value}} for every group and dataset"""
+    with open(path, "rb") as f:
+        data = f.read()
+    p = _Parser(data)
+    datasets, attrs = {}, {}
+    p.walk(p.root_header, "", datasets, attrs)
+    return attrs
 
 
 def structure(path):

@@ -69,6 +69,9 @@ def test_python_reader_against_libhdf5_file():
     assert list(ds) == ["testdouble"] and attrs == {}
     assert ds["testdouble"].shape == (9, 1)
     assert np.array_equal(ds["testdouble"][:, 0], np.arange(9) * np.pi / 4)
+    # the attribute libhdf5 attached to the dataset: pins the attribute-message layout
+    # (name / datatype / dataspace each padded to 8, scalar dataspace, fixed string type)
+    assert h5lite.read_attrs(LIBHDF5_FILE) == {"testdouble": {"MATLAB_class": b"double"}}
     st = h5lite.structure(LIBHDF5_FILE)
     # the conventions the writer copies: K values, cached root scratch pad, heap free list
     assert (st["leaf_k"], st["internal_k"], st["root_cache_type"]) == (4, 16, 1)
