@@ -8,7 +8,7 @@
 //   groups        = object header v1 + symbol-table message (0x11) -> v1 B-tree ("TREE",
 //                   node type 0) -> symbol-table nodes ("SNOD") + local heap ("HEAP")
 //   datasets      = object header v1 with dataspace v1 (0x01), datatype v1 (0x03),
-//                   fill value v2 (0x05), layout v3 CONTIGUOUS (0x08)
+//                   fill value v1 (0x05), layout v3 CONTIGUOUS (0x08)
 //   attributes    = attribute message v1 (0x0c) in the root group's object header
 //   strings       = variable-length string (datatype class 9) through a global heap
 //                   collection ("GCOL"), as snapshot.cc:41-47 writes the RNG state
@@ -244,8 +244,9 @@ private:
     Buf m;
     message(m, 0x0001, dataspace_msg(it.dims));
     message(m, 0x0003, datatype_msg(it.dtype), 1);
-    { // fill value v2: allocate late, write if set, default (zero-length) value defined
-      Buf b; b.u8(2); b.u8(2); b.u8(2); b.u8(1); b.u32(0);
+    { // fill value: allocate late, write if set, default (zero-length) value defined — the
+      // very bytes libhdf5 wrote for the contiguous dataset of the fixture (version 1)
+      Buf b; b.u8(1); b.u8(2); b.u8(2); b.u8(1); b.u32(0);
       message(m, 0x0005, b.s, 1);
     }
     { // layout v3, class 1 = contiguous

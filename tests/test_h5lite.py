@@ -97,6 +97,9 @@ def test_datatype_message_bytes_equal_libhdf5(tmp_path):
     with open(path, "rb") as f:
         mine = f.read()
     assert f64_msg in mine
+    # ... and the fill-value message (header + body) of its contiguous dataset
+    fill_msg = bytes.fromhex("0500080001000000" "0102020100000000")
+    assert fill_msg in ref and fill_msg in mine
     assert mine[:8] == h5lite.SIGNATURE and struct.unpack_from("<Q", mine, 40)[0] == len(mine)
 
 
