@@ -116,7 +116,7 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.nb = h->nb;
   a.ncell = int(p.ncell);
   a.npairs = h->npairs;
-  a.nslots = h->nslots;
+  a.list_cap = hmc_list_capacity(h->nb, h->group);
   a.nstates = h->nstates;
   a.l = p.length;
   a.inv_l = 1.0 / p.length;       // Box, box.h:15
@@ -133,11 +133,22 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.s_out_tab[0] = a.near_max2;
   a.s_out_tab[1] = a.nnear_max2;
   a.s_out_tab[2] = a.rh2;
+  a.s_mid_tab[0] = 0.5 * (a.near_min2 + a.near_max2);
+  a.s_mid_tab[1] = 0.5 * (a.nnear_min2 + a.nnear_max2);
   a.sigma2_tab[0] = a.near_min2;
   a.sigma2_tab[1] = a.near_max2;
   a.sigma2_tab[2] = a.nnear_min2;
   a.sigma2_tab[3] = a.nnear_max2;
   a.sigma2_tab[4] = a.rh2;
+  a.one = 1.0;
+  a.cell_masks = p.ncell <= 10 ? 1 : 0;
+  if (const char *cm = getenv("HMC_CELL_MASKS")) a.cell_masks = a.cell_masks && atoi(cm) != 0; // test knob
+  for (unsigned c = 0; c < 16; c++) {
+    const unsigned nc = p.ncell;
+    a.nbr_tab[c] = (a.cell_masks && c < nc)
+                       ? uint16_t((1u << c) | (1u << ((c + 1) % nc)) | (1u << ((c + nc - 1) % nc)))
+                       : uint16_t(0);
+  }
   a.m = p.m;
   a.vsigma = std::sqrt(p.temp / p.m);
   a.del_t = p.del_t;
@@ -185,7 +196,7 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.md_draw_base = h->md_draws;
   a.mc_draw_base = h->mc_draws;
   a.work_counter = h->d_work;
-  a.smem_per_replica = uint32_t(hmc_smem_per_replica(h->nb));
+  hmc_smem_layout(h->nb, h->group, &a.off_tnn, &a.off_list, &a.off_plist, &a.smem_per_replica);
   a.short_chain = (double(h->nb - 1) * p.near_max < 1.45 * p.length) ? 1 : 0;
   a.chain_max = double(h->nb - 1) * p.near_max;
   {
@@ -366,7 +377,8 @@ int hmc_create(const hmc_params *tr, int n_transitions, int replicas_per_transit
   std::vector<uchar2> pair_ij(np);
   for (int i = 0, q = 0; i < nb; i++)
     for (int j = i + 1; j < nb; j++, q++) pair_ij[q] = make_uchar2((unsigned char)i, (unsigned char)j);
-  std::vector<uint8_t> pairinfo(size_t(h->T) * np, 0);
+  const size_t pstride = size_t(nb) * 64; // symmetric [nb][64] matrix per transition
+  std::vector<uint8_t> pairinfo(size_t(h->T) * pstride, 0);
   std::vector<unsigned long long> bondmask(size_t(h->T) * nb, 0ull);
   std::vector<TransDev> trans(h->T);
   for (int t = 0; t < h->T; t++) {
@@ -395,7 +407,8 @@ int hmc_create(const hmc_params *tr, int n_transitions, int replicas_per_transit
         uint8_t info = 0;
         if (tbk >= 0) info |= uint8_t(tbk + 1);
         if (pbk >= 0) info |= 0x80u;
-        pairinfo[size_t(t) * np + q] = info;
+        pairinfo[size_t(t) * pstride + size_t(i) * 64 + j] = info;
+        pairinfo[size_t(t) * pstride + size_t(j) * 64 + i] = info;
         if (info) {
           bondmask[size_t(t) * nb + i] |= 1ull << j;
           bondmask[size_t(t) * nb + j] |= 1ull << i;

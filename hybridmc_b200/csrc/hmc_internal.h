@@ -28,19 +28,27 @@ enum { HMC_OP_RUN = 0, HMC_OP_MD_ONLY = 1, HMC_OP_CRANK_ONLY = 2 };
 // Kernel argument block (passed by value, __grid_constant__).
 struct KArgs {
   // geometry / potential shared by all transitions
-  int nb, ncell, npairs, nslots, nstates;
+  int nb, ncell, npairs, nstates;
+  int list_cap; // capacity of the per-replica list of live nonlocal predictions (multiple of 8)
+  uint32_t off_tnn, off_list, off_plist; // byte offsets inside a replica's shared-memory image
   double l, inv_l, lcell, inv_lcell;
   double near_min2, near_max2, nnear_min2, nnear_max2, rh2;
   // lookup tables (constant-bank indexed loads instead of select chains)
   double s_in_tab[3];   // inner radius^2 by pair class: nearest, next-nearest, nonlocal core
   double s_out_tab[3];  // outer radius^2 by pair class (nonlocal entry unused)
+  double s_mid_tab[2];  // (inner^2 + outer^2) / 2 of the two local wells
   double sigma2_tab[5]; // wall radius^2 by event type 0..4
+  // ncell <= 10: cells as one-hot masks, 10 bits per axis; nbr_tab[c] = bits c-1, c, c+1
+  // (periodic)
+  int cell_masks;
+  uint16_t nbr_tab[16];
+  double one;       // 1.0 (an operand the compiler cannot fold, see predict_pair)
   double m, vsigma; // vsigma = sqrt(temp/m), init_vel (hardspheres.cc:202)
   double del_t, del_t_wl, gamma0;
   uint32_t nsteps, nsteps_eq, nsteps_wl, write_step, mc_moves, mc_write;
   // tables
   const TransDev *trans;
-  const uint8_t *pairinfo; // [T][npairs]: bits 0-6 transient bit index+1, bit 7 permanent
+  const uint8_t *pairinfo; // [T][nb][64] (symmetric): bits 0-6 transient bit index+1, bit 7 permanent
   const unsigned long long *bondmask; // [T][nb]: bit k set iff pairinfo of (b,k) is non-zero
   const uchar2 *pair_ij;   // [npairs] -> (i,j), i<j
   // ensemble
@@ -101,7 +109,10 @@ struct KArgs {
 // launcher implemented in hmc_kernels.cu; group = lanes per replica (8/16/32)
 cudaError_t hmc_launch(const KArgs &a, int group, cudaStream_t stream, int *grid_out,
                        int *block_out);
-size_t hmc_smem_per_replica(int nb);
+size_t hmc_smem_per_replica(int nb, int group);
+int hmc_list_capacity(int nb, int group);
+void hmc_smem_layout(int nb, int group, uint32_t *off_tnn, uint32_t *off_list, uint32_t *off_plist,
+                     uint32_t *total);
 int hmc_pick_group(int nb);
 
 // message returned by hmc_last_error(NULL) (handle-less entry points)

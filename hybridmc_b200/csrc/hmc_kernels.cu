@@ -9,17 +9,28 @@
 //     because partial-mask __syncwarp/__shfl_sync compile to a slow MATCH/REDUX/BRA.DIV
 //     sequence on sm_100a.  Warps pull batches of replicas from a global work counter,
 //     so there is no barrier between warps (event counts per step vary by 10-70 %).
-//   * the replica lives in shared memory as SoA bead arrays (x,y,z,vx,vy,vz,clock),
-//     per-bead 3-D cell indices and an EVENT TABLE with one slot per bead (its next
-//     cell crossing) and one slot per bead pair (its next predicted collision, with
-//     the event type latched at prediction time).  It replaces the reference's
-//     std::priority_queue + per-bead collision counters (src/event.h:15-116):
-//       - executing a collision (i,j) rewrites every slot touching i or j  (= the
-//         counter bump that invalidates queued events, hardspheres.cc:1118-1119)
+//   * the replica lives in shared memory as bead records (x,y,z,vx,vy,vz,clock, packed
+//     3-D cell index) and an EVENT TABLE that holds, per bead pair, its next predicted
+//     collision with the event type latched at prediction time, and per bead its next
+//     cell crossing.  It replaces the reference's std::priority_queue + per-bead
+//     collision counters (src/event.h:15-116).  The table is stored in two parts:
+//       - DENSE slots for the events that always exist: one cell-wall time per bead and
+//         one time per local pair (k,k+1), (k,k+2) — 3 nb - 3 slots, inside / next to
+//         the bead records;
+//       - a compact LIST of the nonlocal pairs that currently have an event (time +
+//         key = pair and latched type).  Of the nb^2/2 nonlocal pairs only ~0.5 nb are
+//         live at any time (measured: 21 of 946 for crambin, max 70 in 4e5 events), so
+//         the list is scanned in one or two lane strides where a dense pair table
+//         needs nb^2/2G.
+//     Semantics:
+//       - executing a collision (i,j) deletes every list entry touching i or j, rewrites
+//         their local-pair slots and appends the new predictions that have an event
+//         (= the counter bump that invalidates queued events, hardspheres.cc:1118-1119)
 //       - executing a cell crossing of i only min-merges predictions for the beads
-//         in the 9 newly adjacent cells and replaces i's cell slot; all other slots
+//         in the 9 newly adjacent cells and replaces i's cell slot; all other entries
 //         touching i are kept (no counter bump, hardspheres.cc:1622-1645)
-//       - the next event is a lane-parallel argmin over the table + shuffle reduce.
+//       - the next event is a lane-parallel argmin over dense slots + list and a
+//         shuffle reduce; ties go to the lowest (cells, then pairs in (i,j) order) key.
 //     SURVEY.md §7a shows this is bit-identical to the heap; it does none of the
 //     87-90 % stale-pop work of the reference.
 //   * predictions are made exactly when and for whom the reference makes them
@@ -45,39 +56,63 @@
 #define HMC_MIN_BLOCKS 4
 #endif
 
+// The once-per-interval pieces (initialize_system, sampling, crankshaft) are inlined into
+// the kernel; -DHMC_OUTLINE_COLD keeps them out of line (measured on B200: 2-4 % slower,
+// the crankshaft block 3x slower — profiles/README.md).
+#ifdef HMC_OUTLINE_COLD
+#define HMC_COLD __noinline__
+#else
+#define HMC_COLD __forceinline__
+#endif
+
 namespace {
 
 // ----------------------------------------------------------------- helpers --
 
 // Shared-memory image of one replica.
-//   beads: array-of-structs, BSTRIDE doubles per bead: x y z vx vy vz clock cell(pack) - -
-//          one address computation per bead and four 128-bit loads fetch the whole
-//          record; a stride of 80 B keeps every quarter-warp of such loads conflict-free
+//   beads: array-of-structs, BSTRIDE doubles per bead:
+//            x y z vx vy vz clock [cell | wall] t_cell t_near
+//          one address computation per bead and 128-bit loads fetch the whole record; a
+//          stride of 80 B keeps every quarter-warp of such loads conflict-free
 //          (20 k mod 32 covers all banks for 8 consecutive k).
-//   evt / evty: the event table (time, latched type) — nb cell slots then the pair slots.
+//          word 0 of slot 7: packed cell x | y<<8 | z<<16 | wall<<24 (the wall latched
+//          with the bead's cell-crossing time t_cell); word 1: one-hot image of the cell
+//          for the adjacency test.  t_near: event of the pair (k,k+1).
+//          (The latched type of a local-well event is not stored: at the event the pair
+//          sits on the inner or on the outer wall of its well, which tells them apart.)
+//   tnn:   event time of the pair (k,k+2).
+//   le:    the list of live nonlocal predictions, 16 B each: time, key, pad; slots >= the
+//          list length hold +inf.  key = 1<<24 | lo<<16 | hi<<8 | type; a cell event has
+//          key k<<16.
+// The arrays sit at launch-uniform byte offsets (KArgs::off_*) from the replica's base.
 constexpr int BSTRIDE = 10;
-enum { F_X = 0, F_Y = 1, F_Z = 2, F_VX = 3, F_VY = 4, F_VZ = 5, F_T = 6, F_CELL = 7 };
+enum { F_X = 0, F_Y = 1, F_Z = 2, F_VX = 3, F_VY = 4, F_VZ = 5, F_T = 6, F_CELL = 7, F_TC = 8, F_TN = 9 };
+constexpr unsigned PAIR_KEY = 0x01000000u;
+constexpr int PINFO_STRIDE = 64; // pairinfo is a [nb][64] matrix per transition
 
 struct Smem {
   double *b;   // [nb][BSTRIDE]
-  double *evt; // [nslots]
-  uint8_t *evty;
-  uint8_t *plist;           // [2 nb]: partners that survive the single-precision pre-filter
-  const uint16_t *slot_row; // [nb]: slot(lo,hi) = slot_row[lo] + hi (CTA-shared)
+  double *tnn; // [nb]
+  uint4 *le;   // [list_cap]
+  uint8_t *plist; // [2 nb] + scratch: partners that survive the single-precision pre-filter
   int nb;
 };
 
-__device__ __forceinline__ Smem carve(unsigned char *base, const uint16_t *slot_row, int nb,
-                                      int nslots) {
+__device__ __forceinline__ Smem carve(unsigned char *base, const KArgs &a) {
   Smem s;
-  double *d = reinterpret_cast<double *>(base);
-  s.b = d;
-  s.evt = d + BSTRIDE * nb; // [nslots] + one scratch slot that absorbs predicated-off stores
-  s.evty = reinterpret_cast<uint8_t *>(d + BSTRIDE * nb + nslots + 1);
-  s.plist = s.evty + nslots + 1; // evty: [nslots] + scratch; plist: [2 nb] + scratch
-  s.slot_row = slot_row;
-  s.nb = nb;
+  s.b = reinterpret_cast<double *>(base);
+  s.tnn = reinterpret_cast<double *>(base + a.off_tnn);
+  s.le = reinterpret_cast<uint4 *>(base + a.off_list);
+  s.plist = base + a.off_plist;
+  s.nb = a.nb;
   return s;
+}
+
+__device__ __forceinline__ uint4 le_make(double t, unsigned key) {
+  return make_uint4(unsigned(__double2loint(t)), unsigned(__double2hiint(t)), key, 0u);
+}
+__device__ __forceinline__ double le_time(const uint4 &v) {
+  return __hiloint2double(int(v.y), int(v.x));
 }
 
 #define BX(s, k) ((s).b[BSTRIDE * (k) + F_X])
@@ -87,25 +122,46 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const uint16_t *slot_
 #define BVY(s, k) ((s).b[BSTRIDE * (k) + F_VY])
 #define BVZ(s, k) ((s).b[BSTRIDE * (k) + F_VZ])
 #define BT(s, k) ((s).b[BSTRIDE * (k) + F_T])
-// packed cell index: x | y << 8 | z << 16
+// packed cell index x | y << 8 | z << 16, and in the top byte the wall latched with the
+// bead's cell-crossing time
 #define BCELL(s, k) (reinterpret_cast<unsigned *>((s).b + BSTRIDE * (k) + F_CELL)[0])
+#define BWALLB(s, k) (reinterpret_cast<uint8_t *>((s).b + BSTRIDE * (k) + F_CELL)[3])
+// one-hot image of the cell, 10 bits per axis (ncell <= 10): 1 << x | 1 << (10 + y) | 1 << (20 + z)
+#define BOWN(s, k) (reinterpret_cast<unsigned *>((s).b + BSTRIDE * (k) + F_CELL)[1])
 
-// per-replica register state (uniform across the lanes of a group)
+__device__ __forceinline__ unsigned own_mask(unsigned cx, unsigned cy, unsigned cz) {
+  return (1u << cx) | (1u << (10u + cy)) | (1u << (20u + cz));
+}
+// cells within one step (periodic) of the given cell, per axis, in the layout of own_mask;
+// a bead k sits in the 27-neighbourhood iff popc(nbr & own_k) == 3
+__device__ __forceinline__ unsigned nbr_mask(const KArgs &a, unsigned cx, unsigned cy, unsigned cz) {
+  return unsigned(a.nbr_tab[cx]) | (unsigned(a.nbr_tab[cy]) << 10) | (unsigned(a.nbr_tab[cz]) << 20);
+}
+
+// per-replica register state (uniform across the lanes of a group).  Only what the event
+// loop touches at every event lives here; the bond constants of the transition are read
+// through `tr` where a bond pair is involved, counters of rare events go straight to the
+// global accumulators.  (The loop-invariant state of a replica used to take ~60 of the
+// 128 registers; the compiler paid for it by rematerialising addresses and special
+// registers all over the event loop.)
 struct Rep {
   int r;                 // replica index
+  int trans;             // its transition
   unsigned long long config;
   const TransDev *tr;
-  const uint8_t *pinfo;  // pairinfo row of this replica's transition
+  const uint8_t *pinfo;  // pairinfo matrix of this replica's transition
   const unsigned long long *bmask; // bondmask row
-  double *sb;            // s_bias of this replica (global)
-  double rc2, stair2, p_rc2;
-  unsigned has_stair, has_p_rc, max_nbonds;
   unsigned err;
-  unsigned long long n_coll, n_cell, n_att, n_acc, formed, broken;
-  bool tracing;
-  unsigned moves_done;
-  bool live; // false: a clone filling an idle group of the warp; no global side effects
+  unsigned n_coll, n_cell; // events since the last flush (one MD interval)
+  int nl;                // length of the nonlocal event list
+  unsigned flags;        // REP_LIVE | REP_TRACING
 };
+enum { REP_LIVE = 1u,   // not a clone filling an idle group of the warp: has global side effects
+       REP_TRACING = 2u };
+__device__ __forceinline__ bool rep_live(const Rep &R) { return (R.flags & REP_LIVE) != 0u; }
+__device__ __forceinline__ double *rep_sbias(const KArgs &a, const Rep &R) {
+  return a.s_bias + size_t(R.r) * a.nstates;
+}
 
 // "does any replica group of this warp satisfy p" for a GROUP-UNIFORM predicate: with one
 // group per warp (G == 32) that is p itself and no vote instruction is needed.
@@ -119,12 +175,11 @@ template <int G> __device__ __forceinline__ bool warp_any(bool p) {
   }
 }
 
-template <int G> __device__ __forceinline__ unsigned group_mask() {
+template <int G> __device__ __forceinline__ unsigned group_mask(unsigned wlane) {
   if constexpr (G == 32) {
     return 0xffffffffu;
   } else {
-    const unsigned lane = threadIdx.x & 31u;
-    return ((1u << G) - 1u) << (lane & ~unsigned(G - 1));
+    return ((1u << G) - 1u) << (wlane & ~unsigned(G - 1));
   }
 }
 
@@ -215,6 +270,53 @@ __device__ __forceinline__ void sts_pred_u32(unsigned *ptr, unsigned v, bool p) 
                : "r"(int(p)), "r"(addr), "r"(v)
                : "memory");
 }
+__device__ __forceinline__ void sts_pred_v4(uint4 *ptr, const uint4 &v, bool p) {
+  const unsigned addr = unsigned(__cvta_generic_to_shared(ptr));
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p st.shared.v4.u32 [%1], {%2, %3, %4, %5};\n\t}"
+      :
+      : "r"(int(p)), "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+      : "memory");
+}
+__device__ __forceinline__ void sts_pred_f64(double *ptr, double v, bool p) {
+  const unsigned addr = unsigned(__cvta_generic_to_shared(ptr));
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p st.shared.f64 [%1], %2;\n\t}"
+               :
+               : "r"(int(p)), "r"(addr), "d"(v)
+               : "memory");
+}
+__device__ __forceinline__ void sts_pred_u8(uint8_t *ptr, unsigned v, bool p) {
+  const unsigned addr = unsigned(__cvta_generic_to_shared(ptr));
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p st.shared.u8 [%1], %2;\n\t}"
+               :
+               : "r"(int(p)), "r"(addr), "r"(v)
+               : "memory");
+}
+
+// lane bookkeeping of a replica group inside its warp
+template <int G> struct GroupLanes {
+  unsigned shift; // first lane of the group
+  unsigned bits;  // G ones
+  unsigned below; // ones below this lane (group-relative)
+  __device__ __forceinline__ GroupLanes(int lane, unsigned wlane) { // wlane: lane in the warp
+    shift = wlane & ~unsigned(G - 1);
+    bits = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+    below = (1u << lane) - 1u;
+  }
+  // the group's slice of a full-warp ballot
+  __device__ __forceinline__ unsigned ballot(bool p) const {
+    return (__ballot_sync(0xffffffffu, p) >> shift) & bits;
+  }
+};
+
+// largest value of a group-uniform quantity over the groups of the warp (trip counts)
+template <int G> __device__ __forceinline__ int warp_max(int v) {
+  if constexpr (G == 32) {
+    return v;
+  } else {
+    return int(__reduce_max_sync(0xffffffffu, unsigned(v)));
+  }
+}
 
 // delta_tpv (hardspheres.cc:372-392) followed by the type logic of if_nearest_bond /
 // if_nnearest_bond (:863-923) or if_coll (:425-476).  Returns the latched event type,
@@ -279,11 +381,12 @@ __device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, c
     const unsigned long long tmask = tb ? (1ull << (tb - 1)) : 0ull;
     const bool bonded_t = (R.config & tmask) != 0;
     const bool nonbonded_t = (~R.config & tmask) != 0;
+    const TransDev &T = *R.tr;
     // get_rc2_inner / get_rc2_outer, hardspheres.cc:394-419
-    const double r2i = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
-    double r2o = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
-    r2o = (R.has_stair && nonbonded_t) ? R.stair2 : r2o;
-    const bool capcand = tmask && (unsigned(__popcll(R.config)) < R.max_nbonds) && nonbonded_t;
+    const double r2i = (perm && T.has_p_rc) ? T.p_rc2 : T.rc2;
+    double r2o = (perm && T.has_p_rc) ? T.p_rc2 : T.rc2;
+    r2o = (T.has_stair && nonbonded_t) ? T.stair2 : r2o;
+    const bool capcand = tmask && (unsigned(__popcll(R.config)) < T.max_nbonds) && nonbonded_t;
     // first inner candidate: well minimum (local) / bond radius (capture) / hard core
     const double s_in1 = local ? (near ? a.near_min2 : a.nnear_min2) : (capcand ? r2i : a.rh2);
     const bool hit1 = approaching && (rv2 > vv * (rr - s_in1)); // t_until_inner_coll :217-240
@@ -292,7 +395,7 @@ __device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, c
     inner = hit1 || hit2;
     const double s_out = local ? (near ? a.near_max2 : a.nnear_max2) : r2o;
     s2 = hit1 ? s_in1 : (hit2 ? a.rh2 : s_out);
-    outer_ok = local || bonded_t || perm || (R.has_stair && nonbonded_t);
+    outer_ok = local || bonded_t || perm || (T.has_stair && nonbonded_t);
     if (local) ty = (near ? HMC_EV_MIN_NEAREST : HMC_EV_MIN_NNEAREST) + (inner ? 0u : 1u);
     else ty = hit1 ? (capcand ? HMC_EV_MAX_NONLOCAL_INNER : HMC_EV_MIN_NONLOCAL_INNER)
                    : (hit2 ? HMC_EV_MIN_NONLOCAL_INNER : HMC_EV_MAX_NONLOCAL_OUTER);
@@ -302,7 +405,10 @@ __device__ __forceinline__ unsigned predict_pair(const KArgs &a, const Rep &R, c
   // whole warp through the slow-path subroutines of sqrt / division.
   const bool valid = want && (inner || outer_ok);
   const double rad1 = vv * (rr - s2);
-  const double root = sqrt(valid ? rv2 - rad1 : 1.0);
+  // (the harmless operand is a kernel argument, not a literal: with a literal the compiler
+  // turns sqrt(valid ? x : 1.0) into valid ? sqrt(x) : 1.0 and the unused lanes' zero or
+  // negative radicands take the slow path after all)
+  const double root = sqrt(valid ? rv2 - rad1 : a.one);
   const double num = inner ? (-rv - root) : (-rv + root); // :237 / :253
   tout = ti + (valid ? num : 1.0) / (valid ? vv : 1.0);
   return valid ? ty : 0xffu;
@@ -407,6 +513,7 @@ struct WordStream { // crankshaft word source: injected tape or Philox
   unsigned c1, c2, c3; // counter words 1..3
   uint4 buf;
   unsigned buf_blk;
+  unsigned moves_done;
 };
 
 __device__ __forceinline__ unsigned ws_next(WordStream &w) {
@@ -448,7 +555,7 @@ __device__ __forceinline__ unsigned ws_uniform_int(WordStream &w, unsigned lo, u
 
 __device__ __forceinline__ void trace_event(const KArgs &a, const Rep &R, int lane, unsigned type,
                                             unsigned i, unsigned j, double t) {
-  if (R.tracing && R.live && lane == 0) {
+  if (R.flags == (REP_LIVE | REP_TRACING) && lane == 0) {
     const unsigned n = *a.trace_n;
     if (n < a.trace_cap) {
       hmc_event e;
@@ -473,7 +580,92 @@ __device__ __forceinline__ double hamiltonian(const KArgs &a, const Rep &R, cons
     const double vz2 = BVZ(s, i) * BVZ(s, i);
     ke += hm * (vx2 + vy2 + vz2);
   }
-  return ke + R.sb[R.config];
+  return ke + rep_sbias(a, R)[R.config];
+}
+
+// ------------------------------------------------------------ event table --
+
+// what an out-of-line step piece changes in the replica registers
+struct StepOut {
+  unsigned err;
+  int nl;
+};
+
+// Cell crossing: keep the earlier of the queued and the new event of a pair
+// (add_events_for_bead_after_crossing, hardspheres.cc:740-856: the older event stays
+// queued, so the earlier of the two fires).  Rare — a crossing predicts ~4 partners and one
+// in ten has an event — and therefore out of line.  Executed by the whole warp.
+template <int G>
+__device__ __noinline__ StepOut list_merge(const KArgs &a, const Smem &s_in, int nl, unsigned err,
+                                           bool mrg, double tt, unsigned key, int lane,
+                                           unsigned wlane) {
+  const Smem s = s_in;
+  const GroupLanes<G> gl(lane, wlane);
+  unsigned pend = gl.ballot(mrg);
+  while (__any_sync(0xffffffffu, pend != 0u)) {
+    const bool act = pend != 0u;
+    const int src = int(gl.shift) + (act ? __ffs(int(pend)) - 1 : 0);
+    const double ct = __shfl_sync(0xffffffffu, tt, src);
+    const unsigned ck = __shfl_sync(0xffffffffu, key, src);
+    bool found = false;
+    const int nmax = warp_max<G>(nl);
+    for (int base = 0; base < nmax; base += G) {
+      const int e = base + lane;
+      const uint4 v = s.le[e];
+      const bool m = act && e < nl && ((v.z ^ ck) & 0xffffff00u) == 0u;
+      if (m && ct < le_time(v)) s.le[e] = le_make(ct, ck);
+      found |= m;
+    }
+    const unsigned fb = gl.ballot(found);
+    if (act && fb == 0u) {
+      if (nl < a.list_cap) {
+        if (lane == 0) s.le[nl] = le_make(ct, ck);
+        nl++;
+      } else {
+        err |= HMC_ERR_LIST_OVERFLOW;
+      }
+    }
+    pend &= pend - 1u;
+    __syncwarp();
+  }
+  StepOut out;
+  out.err = err;
+  out.nl = nl;
+  return out;
+}
+
+// Store one prediction the reference made for the pair (b,k) (`on`; pty == 0xff: the
+// reference queues nothing).  Local wells go to their dense slot; a nonlocal event is
+// appended to the list after a collision (every older entry of the two beads is dropped
+// by the sweep of next_event that ends the event) or min-merged into it at a cell crossing.  Executed by the
+// whole warp.
+template <int G>
+__device__ __forceinline__ void commit_prediction(const KArgs &a, Rep &R, const Smem &s, bool on,
+                                                  int b, int k, unsigned pty, double tt,
+                                                  bool is_cell, int lane,
+                                                  const GroupLanes<G> &gl) {
+  const int lo = min(b, k), hi = max(b, k), d = hi - lo;
+  const bool have = on && pty != 0xffu;
+  // local wells: collisions only (a crossing predicts nonlocal partners only), always an event
+  double *dense = d == 1 ? s.b + BSTRIDE * lo + F_TN : s.tnn + lo;
+  if (have && d < 3) *dense = tt;
+  const bool nl = have && d >= 3;
+  const unsigned key = PAIR_KEY | (unsigned(lo) << 16) | (unsigned(hi) << 8) | pty;
+  // collision: append behind the surviving entries
+  const bool app = nl && !is_cell;
+  const unsigned gb = gl.ballot(app);
+  const int dst = R.nl + __popc(gb & gl.below);
+  const int nnew = R.nl + __popc(gb);
+  if (app && dst < a.list_cap) s.le[dst] = le_make(tt, key);
+  if (nnew > a.list_cap) R.err |= HMC_ERR_LIST_OVERFLOW;
+  R.nl = min(nnew, a.list_cap);
+  const bool mrg = nl && is_cell;
+  if (__any_sync(0xffffffffu, mrg)) {
+    const Smem sc = s; // (a copy: the address of s itself must not escape)
+    const StepOut mo = list_merge<G>(a, sc, R.nl, R.err, mrg, tt, key, lane, gl.shift + unsigned(lane));
+    R.nl = mo.nl;
+    R.err = mo.err;
+  }
 }
 
 // --------------------------------------------------- step initialisation --
@@ -501,6 +693,10 @@ template <int G>
 __device__ __forceinline__ unsigned check_constraints(const KArgs &a, const Rep &R, const double *P,
                                                       bool strict, int lane, unsigned gmask) {
   bool lok = true, nok = true;
+  // bond constants of the transition, read once (not per pair)
+  const double perm_r2 = R.tr->has_p_rc ? R.tr->p_rc2 : R.tr->rc2;
+  const bool has_stair = R.tr->has_stair != 0u;
+  const double stair2 = R.tr->stair2;
   for (int p = lane; p < a.npairs; p += G) {
     const uchar2 ij = __ldg(&a.pair_ij[p]);
     const int i = ij.x, j = ij.y, d = j - i;
@@ -517,13 +713,10 @@ __device__ __forceinline__ unsigned check_constraints(const KArgs &a, const Rep 
       lok = lok && ok;
     } else {
       const double d2 = dist2_ij(a, P, i, j);
-      const unsigned info = __ldg(&R.pinfo[p]);
+      const unsigned info = __ldg(&R.pinfo[i * PINFO_STRIDE + j]);
       bool ok = d2 > a.rh2;
-      if (info & 0x80u) {
-        const double r2i = R.has_p_rc ? R.p_rc2 : R.rc2;
-        ok = ok && (d2 < r2i);
-      }
-      if (R.has_stair && (info & 0x7fu)) ok = ok && (d2 < R.stair2);
+      if (info & 0x80u) ok = ok && (d2 < perm_r2);
+      if (has_stair && (info & 0x7fu)) ok = ok && (d2 < stair2);
       nok = nok && ok;
     }
   }
@@ -534,11 +727,19 @@ __device__ __forceinline__ unsigned check_constraints(const KArgs &a, const Rep 
 
 // initialize_system, main.cc:45-95: constraint checks, init_cells, velocities
 // (+ COM shift), and the full prediction fill of the event table.
-template <int G, bool SC>
 // Executed by the whole warp; only groups with `on` change their state (the others are in
-// the middle of a step).
-__device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *normals,
-                          unsigned long long draw, int lane, unsigned gmask, bool on) {
+// the middle of a step).  Once per MD interval: kept out of line, the event loop's
+// instruction footprint is what the instruction cache has to hold.
+// Out-of-line pieces take the replica registers and the shared-memory pointers by const
+// reference (the caller's copy) and work on local copies; what they change comes back by
+// value — a reference into the caller's frame would turn every access into a local-memory
+// load.
+template <int G, bool SC>
+__device__ HMC_COLD StepOut init_step(const KArgs &a, const Rep &R_in, const Smem &s_in,
+                                          const double *normals, unsigned long long draw, int lane,
+                                          unsigned wlane, unsigned gmask, bool on) {
+  Rep R = R_in;
+  const Smem s = s_in;
   const int nb = a.nb;
   const unsigned ok = check_constraints<G>(a, R, s.b + F_X, false, lane, gmask);
   if (on && !(ok & 1u)) R.err |= HMC_ERR_LOCAL_OVERLAP;
@@ -556,6 +757,7 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
     iy = min(max(iy, 0), hi);
     iz = min(max(iz, 0), hi);
     BCELL(s, k) = unsigned(ix) | (unsigned(iy) << 8) | (unsigned(iz) << 16);
+    BOWN(s, k) = own_mask(min(unsigned(ix), 9u), min(unsigned(iy), 9u), min(unsigned(iz), 9u)); // (used iff ncell <= 10)
     double nx, ny, nz;
     if (a.rng_mode == HMC_RNG_INJECTED) {
       nx = normals[3 * k + 0];
@@ -601,17 +803,24 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
   }
   __syncwarp();
 
+  // empty event list
+  R.nl = on ? 0 : R.nl;
   // init_cell_events (hardspheres.cc:696-704)
   for (int k = lane; k < nb && on; k += G) {
     const Bead b = load_bead(s, k);
     double t;
     unsigned wall = 0;
     const unsigned ck = BCELL(s, k);
-    const bool cr = predict_cell(a, b, int(ck & 0xffu), int((ck >> 8) & 0xffu), int(ck >> 16), t, wall);
-    s.evt[k] = cr ? t : CUDART_INF;
-    s.evty[k] = uint8_t(wall);
+    const bool cr = predict_cell(a, b, int(ck & 0xffu), int((ck >> 8) & 0xffu), int((ck >> 16) & 0xffu), t, wall);
+    s.b[BSTRIDE * k + F_TC] = cr ? t : CUDART_INF;
+    BWALLB(s, k) = uint8_t(wall);
+    // the last beads have no (k,k+1) / (k,k+2) partner
+    if (k >= nb - 1) s.b[BSTRIDE * k + F_TN] = CUDART_INF;
+    if (k >= nb - 2) s.tnn[k] = CUDART_INF;
   }
+  __syncwarp();
   // init_nearest/nnearest_bond_events (:885-937) and add_events_for_all_beads (:540-555)
+  const GroupLanes<G> gl(lane, wlane);
   for (int base = 0; base < a.npairs; base += G) {
     const int p = min(base + lane, a.npairs - 1); // every lane calls predict_pair
     const bool mine = base + lane < a.npairs;
@@ -622,52 +831,84 @@ __device__ void init_step(const KArgs &a, Rep &R, const Smem &s, const double *n
       doit = mine && (adj_mask(BCELL(s, i), BCELL(s, j), unsigned(a.ncell - 1) * 0x00010101u) &
                       0x00ffffffu) == 0x00ffffffu;
     double tt;
-    const unsigned ty = predict_pair<SC>(a, R, s, i, j, true, d, __ldg(&R.pinfo[p]), doit && on, tt);
-    if (mine && on) {
-      s.evt[nb + p] = (ty != 0xffu) ? tt : CUDART_INF;
-      s.evty[nb + p] = uint8_t(ty);
-    }
+    const unsigned ty = predict_pair<SC>(a, R, s, i, j, true, d,
+                                         __ldg(&R.pinfo[i * PINFO_STRIDE + j]), doit && on, tt);
+    commit_prediction<G>(a, R, s, doit && on, i, j, ty, tt, false, lane, gl);
   }
   __syncwarp();
+  StepOut out;
+  out.err = R.err;
+  out.nl = R.nl;
+  return out;
 }
 
 // --------------------------------------------------------- the event loop --
 
-// Lane-strided argmin over the event table of the group + shuffle reduce
-// (ties -> lowest slot).  Replaces EventQueue::top() (event.h:105-116).
+// Next event of the replica: lane-strided minimum over the dense slots (cell walls, local
+// wells) and the nonlocal list + shuffle reduce.  Ties go to the lowest key, i.e. cell
+// events by bead first, then pairs in (i,j) order.  Replaces EventQueue::top()
+// (event.h:105-116).
+// The same sweep over the list finishes a collision of (bi,bj) (`coll`): that collision
+// invalidated every event the two beads had queued (the counter bump,
+// hardspheres.cc:1118-1119), i.e. the list entries below n_old that touch bi or bj — the
+// entries from n_old on are the predictions just made.  They are dropped and the rest is
+// compacted in place, keeping its order.  Executed by the whole warp.
 template <int G>
-__device__ __forceinline__ void table_argmin(const Smem &s, int nslots, int lane, double &bt,
-                                             int &bs) {
-  bt = CUDART_INF;
-  bs = 0x7fffffff;
-  // group-uniform trip counts: full strides first (pointer + immediate offsets once
-  // unrolled), then one clamped stride whose tail lanes re-read the last slot (same time,
-  // same index)
-  const double *col = s.evt + lane;
-  int q = lane;
-  const int nfull = nslots - G;
-#pragma unroll 4
-  for (int base = 0; base <= nfull; base += G) {
-    const double t = col[base];
-    const bool lt = t < bt;
-    bt = lt ? t : bt;
-    bs = lt ? q : bs;
-    q += G;
+__device__ __forceinline__ void next_event(const Smem &s, Rep &R, bool coll, int bi, int bj,
+                                           int n_old, int lane, const GroupLanes<G> &gl,
+                                           double &bt, unsigned &bk) {
+  const int nb = s.nb;
+  double ct = CUDART_INF, pt = CUDART_INF;
+  unsigned ck = 0u, pk = 0xffffffffu;
+  // dense slots, one bead per lane; group-uniform trip count, tail lanes re-read the last
+  // bead (same times, same keys).  Cells and pairs keep separate minima: within each the
+  // keys come in ascending order, so a strict '<' keeps the lowest key of a tie.
+  for (int base = 0; base < nb; base += G) {
+    const int k = min(base + lane, nb - 1);
+    const double2 d = *reinterpret_cast<const double2 *>(s.b + BSTRIDE * k + F_TC);
+    const double t2 = s.tnn[k];
+    const unsigned kb = unsigned(k) * 0x00010100u; // k << 16 | k << 8
+    const bool l0 = d.x < ct;
+    ct = l0 ? d.x : ct;
+    ck = l0 ? unsigned(k) << 16 : ck;
+    const bool l1 = d.y < pt;
+    pt = l1 ? d.y : pt;
+    pk = l1 ? kb + (PAIR_KEY | 0x100u) : pk; // (k, k+1)
+    const bool l2 = t2 < pt;
+    pt = l2 ? t2 : pt;
+    pk = l2 ? kb + (PAIR_KEY | 0x200u) : pk; // (k, k+2)
   }
-  {
-    q = min(q, nslots - 1);
-    const double t = s.evt[q];
-    const bool lt = t < bt;
-    bt = lt ? t : bt;
-    bs = lt ? q : bs;
+  // nonlocal list: unordered, so the full tie rule
+  const int nl = R.nl;
+  const int nmax = warp_max<G>(nl);
+  const unsigned pi = unsigned(bi) * 0x00010100u, pj = unsigned(bj) * 0x00010100u;
+  int nk = 0;
+  for (int base = 0; base < nmax; base += G) {
+    const int e = base + lane;
+    const uint4 v = s.le[e];
+    const unsigned x = v.z & 0x00ffff00u; // lo, hi
+    const bool touch = ((__vcmpeq4(x, pi) | __vcmpeq4(x, pj)) & 0x00ffff00u) != 0u;
+    const bool keep = e < nl && !(coll && e < n_old && touch);
+    const unsigned gb = gl.ballot(keep);
+    const int dst = nk + __popc(gb & gl.below); // dst <= e: never ahead of the reads
+    sts_pred_v4(s.le + dst, v, keep && coll);    // (without a collision nothing moves)
+    nk += __popc(gb);
+    const double t = le_time(v);
+    const bool lt = keep && ((t < pt) | ((t == pt) & (v.z < pk)));
+    pt = lt ? t : pt;
+    pk = lt ? v.z : pk;
   }
+  R.nl = nk;
+  const bool tp = pt < ct; // a cell event wins a tie against any pair
+  bt = tp ? pt : ct;
+  bk = tp ? pk : ck;
 #pragma unroll
   for (int off = G / 2; off > 0; off >>= 1) {
     const double ot = __shfl_xor_sync(0xffffffffu, bt, off);
-    const int os = __shfl_xor_sync(0xffffffffu, bs, off);
-    const bool take = (ot < bt) | ((ot == bt) & (os < bs)); // (no short-circuit branches)
+    const unsigned ok = __shfl_xor_sync(0xffffffffu, bk, off);
+    const bool take = (ot < bt) | ((ot == bt) & (ok < bk)); // (no short-circuit branches)
     bt = take ? ot : bt;
-    bs = take ? os : bs;
+    bk = take ? ok : bk;
   }
 }
 
@@ -677,26 +918,29 @@ __device__ __forceinline__ void table_argmin(const Smem &s, int nslots, int lane
 // The body is one instruction path for collisions and cell crossings alike (selects
 // instead of branches): the replica groups that share a warp execute it together, and
 // a crossing simply discards the collision arithmetic it did not need.
-template <int G, bool SC>
+template <int G, bool SC, bool TP>
 __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s, bool has,
-                                           double bt, int bs, int lane) {
+                                           double &bt_io, unsigned &bk_io, int lane,
+                                           const GroupLanes<G> &gl) {
   const int nb = a.nb, nc = a.ncell;
   {
-    bs = has ? bs : 0;
+    const double bt = bt_io;
+    const unsigned bk = has ? bk_io : 0u;
+    const int n_old = R.nl; // list entries that predate this event
 
     const double t = bt;
-    const bool is_cell = bs < nb;
+    const bool is_cell = bk < PAIR_KEY;
     const int nbead = is_cell ? 1 : 2; // beads whose slots are re-predicted
-    const int pidx = is_cell ? 0 : bs - nb;
-    const uchar2 ij = __ldg(&a.pair_ij[pidx]);
-    const int bi = is_cell ? bs : int(ij.x);
-    const int bj = is_cell ? bs : int(ij.y);
-    const unsigned ty = s.evty[bs]; // latched type, or the wall of a crossing
-    const unsigned wall = is_cell ? ty : 0u;
+    const int bi = int((bk >> 16) & 0xffu);
+    const int bj = is_cell ? bi : int((bk >> 8) & 0xffu);
+    const int pidx = bi * PINFO_STRIDE + bj;
+    const int dij = bj - bi;
+    // the wall latched at the prediction of a crossing (t_until_cell :589-666)
+    const unsigned wall = is_cell ? unsigned(BWALLB(s, bi)) : 0u;
 
     Bead I = load_bead(s, bi), J = load_bead(s, bj);
     const unsigned ci0 = BCELL(s, bi);
-    int cxn = int(ci0 & 0xffu), cyn = int((ci0 >> 8) & 0xffu), czn = int(ci0 >> 16);
+    int cxn = int(ci0 & 0xffu), cyn = int((ci0 >> 8) & 0xffu), czn = int((ci0 >> 16) & 0xffu);
     // BeadCellEvent (hardspheres.cc:1622-1645): new cell from the wall latched at
     // prediction (t_until_cell :589-666)
     if (is_cell) {
@@ -719,23 +963,43 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
     // collision events, hardspheres.cc:1106-1620: final_vel (:1050-1061)
     double dx = J.x - I.x, dy = J.y - I.y, dz = J.z - I.z;
     mindist3_t<SC>(a, dx, dy, dz);
-    const unsigned info = is_cell ? 0u : unsigned(__ldg(&R.pinfo[pidx]));
-    const unsigned tb = info & 0x7fu;
-    const bool perm = (info & 0x80u) != 0;
-    const unsigned long long tmask = tb ? (1ull << (tb - 1)) : 0ull;
-    const double r2p = (perm && R.has_p_rc) ? R.p_rc2 : R.rc2;
+    // latched event type: in the key for a nonlocal pair; a local-well event happens ON the
+    // inner or the outer wall of the well (radii 15 % apart), so the separation at the
+    // event tells which one was latched; for a crossing: the wall
+    const int cls = min(dij, 2) - 1;
+    const bool on_inner = dx * dx + dy * dy + dz * dz < a.s_mid_tab[max(cls, 0)];
+    const unsigned ty = is_cell ? wall
+                                : (dij >= 3 ? (bk & 0xffu) : unsigned(2 * cls) + (on_inner ? 0u : 1u));
     // radius of the wall that was hit
     double sigma2 = a.sigma2_tab[min(ty, 4u)];
-    sigma2 = ty == HMC_EV_MAX_NONLOCAL_INNER ? r2p : sigma2; // :1462-1466
-    if (ty == HMC_EV_MAX_NONLOCAL_OUTER)                     // :1548-1552
-      sigma2 = (R.has_stair && (~R.config & tmask)) ? R.stair2 : r2p;
-    sigma2 = (is_cell || !has) ? 1.0 : sigma2;
-    // entropy step of bond events: s_of_inner_event :299-313 / s_of_outer_event :317-331
-    const bool capture = !is_cell && ty == HMC_EV_MAX_NONLOCAL_INNER;
-    const bool escape = !is_cell && ty == HMC_EV_MAX_NONLOCAL_OUTER && tmask && (R.config & tmask);
-    const bool has_dS = capture || escape;
+    // bond events (capture at the bond radius / the outer wall of a bond, a staircase or a
+    // permanent bond) are rare: their constants are read from the transition's table inside
+    // a warp-uniform branch
+    const bool bondev = has && !is_cell && ty >= HMC_EV_MAX_NONLOCAL_INNER;
+    unsigned long long tmask = 0ull;
+    bool capture = false, has_dS = false;
     double dS = 0.0;
-    if (has_dS) dS = R.sb[unsigned(R.config ^ tmask)] - R.sb[unsigned(R.config)];
+    if (__any_sync(0xffffffffu, bondev)) {
+      const unsigned info = bondev ? unsigned(__ldg(&R.pinfo[pidx])) : 0u;
+      const unsigned tb = info & 0x7fu;
+      const bool perm = (info & 0x80u) != 0;
+      tmask = tb ? (1ull << (tb - 1)) : 0ull;
+      const TransDev &T = *R.tr;
+      const double r2p = (perm && T.has_p_rc) ? T.p_rc2 : T.rc2;
+      double s2b = r2p;                                   // MaxNonlocalInner :1462-1466
+      if (ty == HMC_EV_MAX_NONLOCAL_OUTER)                // :1548-1552
+        s2b = (T.has_stair && (~R.config & tmask)) ? T.stair2 : r2p;
+      sigma2 = bondev ? s2b : sigma2;
+      // entropy step of bond events: s_of_inner_event :299-313 / s_of_outer_event :317-331
+      capture = bondev && ty == HMC_EV_MAX_NONLOCAL_INNER;
+      const bool escape = bondev && ty == HMC_EV_MAX_NONLOCAL_OUTER && tmask && (R.config & tmask);
+      has_dS = capture || escape;
+      if (has_dS) {
+        const double *sb = rep_sbias(a, R);
+        dS = sb[unsigned(R.config ^ tmask)] - sb[unsigned(R.config)];
+      }
+    }
+    sigma2 = (is_cell || !has) ? 1.0 : sigma2;
     // v_after_coll (:258-295)
     const double dvx = J.vx - I.vx, dvy = J.vy - I.vy, dvz = J.vz - I.vz;
     const double mu = 0.5 * a.m;
@@ -761,10 +1025,11 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
       J.vy -= py / 2;
       J.vz -= pz / 2;
     }
-    if (transmitted && has) {
+    if (transmitted && has) { // (only inside a bond event: rare)
       R.config ^= tmask;
-      if (capture) R.formed++;
-      else R.broken++;
+      // count_bond.formed / broken (:1470-1474, :1556-1560)
+      if (lane == 0 && rep_live(R))
+        atomicAdd(&a.acc[size_t(a.n_trans) * a.nstates + (capture ? 0 : a.n_trans) + R.trans], 1ull);
     }
     R.n_cell += (has && is_cell) ? 1u : 0u;
     R.n_coll += (has && !is_cell) ? 1u : 0u;
@@ -772,15 +1037,17 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
     // write the 1-2 event beads back: lane 0 stores bead bi (and its cell), lane 1 bead bj,
     // as predicated 128-bit stores (no divergent branch in the lockstep path)
     store_bead(s.b + BSTRIDE * bi, I, t, has && lane == 0);
-    sts_pred_u32(reinterpret_cast<unsigned *>(s.b + BSTRIDE * bi + F_CELL),
-                 unsigned(cxn) | (unsigned(cyn) << 8) | (unsigned(czn) << 16), has && lane == 0);
+    if (has && lane == 0) { // (the wall byte is rewritten with the new cell time below)
+      BCELL(s, bi) = unsigned(cxn) | (unsigned(cyn) << 8) | (unsigned(czn) << 16);
+      BOWN(s, bi) = own_mask(min(unsigned(cxn), 9u), min(unsigned(cyn), 9u), min(unsigned(czn), 9u));
+    }
     store_bead(s.b + BSTRIDE * bj, J, t, has && lane == 1 && !is_cell);
     if (has) trace_event(a, R, lane, is_cell ? unsigned(HMC_EV_BEAD_CELL) : ty, bi, is_cell ? wall : bj, t);
     __syncwarp();
 
     // ---- re-prediction ----
-    // collision: every slot touching bi or bj is rewritten (local wells always, nonlocal
-    // partners only inside the 27-cell neighbourhood, add_events_for_one_bead :507-536)
+    // collision: the local wells of bi and bj always, nonlocal partners only inside the
+    // 27-cell neighbourhood (add_events_for_one_bead :507-536)
     // crossing: only partners in the 9 newly adjacent cells, min-merged
     // (add_events_for_bead_after_crossing :740-856); plus if_cell for each bead.
 
@@ -791,7 +1058,7 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
       const int qb = lane >= 3 ? 1 : 0, ax = lane - 3 * qb; // lanes 0-2: bead bi, 3-5: bead bj
       const bool on = lane < 6;
       const int b = qb ? bj : bi;
-      const double *rec = s.b + BSTRIDE * b;
+      double *rec = s.b + BSTRIDE * b;
       const int axc = on ? ax : 0;
       const double v_ld = rec[F_VX + axc], p_ld = rec[F_X + axc]; // (unconditional loads)
       const unsigned c_ld = BCELL(s, b);
@@ -814,11 +1081,12 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
         ct = take ? ot : ct;
         cw = take ? ow : cw;
       }
-      // lane 0 now holds bead bi's wall, lane 3 bead bj's (scratch slot for everyone else)
+      // lane 0 now holds bead bi's wall, lane 3 bead bj's
       const bool mine = has && (lane == 0 || (lane == 3 && !is_cell));
-      const int wq = mine ? b : a.nslots;
-      s.evt[wq] = BT(s, b) + ct;
-      s.evty[wq] = uint8_t(cw);
+      if (mine) {
+        rec[F_TC] = rec[F_T] + ct;
+        reinterpret_cast<uint8_t *>(rec + F_CELL)[3] = uint8_t(cw);
+      }
     }
 
     // partner predictions, both beads in one flattened lane loop
@@ -831,7 +1099,15 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
       far += far < 0 ? nc : 0;
       far -= far >= nc ? nc : 0;
       const unsigned others = 0x00ffffffu & ~(0xffu << (8 * axis)); // the two other axes
-      if (!a.two_pass) {
+      // ncell <= 10: which partners the reference predicts, as one mask per event bead
+      // (the 27-neighbourhood of its cell; for a crossing the 9 cells that became adjacent)
+      unsigned probe0 = 0u, probe1 = 0u;
+      if (a.cell_masks) {
+        probe0 = nbr_mask(a, cb0 & 0xffu, (cb0 >> 8) & 0xffu, (cb0 >> 16) & 0xffu);
+        probe1 = nbr_mask(a, cb1 & 0xffu, (cb1 >> 8) & 0xffu, (cb1 >> 16) & 0xffu);
+        if (is_cell) probe0 = (probe0 & ~(0x3ffu << (10u * axis))) | ((1u << far) << (10u * axis));
+      }
+      if (!TP) {
         // short chains: a single pass over all 2 nb candidates (the pre-filter below costs
         // more than the few predictions it would save)
         const int nitem = nbead * nb;
@@ -845,27 +1121,25 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
           const bool in_range = idx < nitem;
           k = in_range ? k : b;
           const int d = abs(b - k);
-          // nb + pair index; an in-range dummy for k == b (never stored)
-          const int slot = k == b ? nb : int(s.slot_row[min(b, k)]) + max(b, k);
-          const unsigned cb = second ? cb1 : cb0, ck = BCELL(s, k);
-          const unsigned am = adj_mask(cb, ck, ncm1x3);
-          // which (b,k) the reference predicts at this event
-          const bool want_cell = d >= 3 && int((ck >> (8 * axis)) & 0xffu) == far &&
-                                 (am & others) == others;
-          const bool want_coll = d < 3 || (am & 0x00ffffffu) == 0x00ffffffu;
-          const bool active = has && in_range && k != b;
-          const bool doit = active && (is_cell ? want_cell : want_coll);
+          const int pq = b * PINFO_STRIDE + k;
+          // which (b,k) the reference predicts at this event: local wells at a collision,
+          // nonlocal partners in the probed cells
+          bool want;
+          if (a.cell_masks) {
+            want = __popc((second ? probe1 : probe0) & BOWN(s, k)) == 3;
+          } else {
+            const unsigned cb = second ? cb1 : cb0, ck = BCELL(s, k);
+            const unsigned am = adj_mask(cb, ck, ncm1x3);
+            want = is_cell ? (int((ck >> (8 * axis)) & 0xffu) == far && (am & others) == others)
+                           : (am & 0x00ffffffu) == 0x00ffffffu;
+          }
+          // (the pair (bi,bj) itself is predicted once, from bi's side)
+          const bool active = has && in_range && k != b && !(second && k == bi);
+          const bool doit = active && (d < 3 ? !is_cell : want);
           double tt;
           const unsigned pty =
-              predict_pair<SC>(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), doit, tt);
-          const bool have = doit && pty != 0xffu;
-          const double tnew = have ? tt : CUDART_INF;
-          // collision: overwrite (or clear) the slot; crossing: keep the earlier of old/new
-          const bool store = active && (is_cell ? (have && tnew < s.evt[slot]) : true);
-          if (store) {
-            s.evt[slot] = tnew;
-            s.evty[slot] = uint8_t(pty);
-          }
+              predict_pair<SC>(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[pq]), doit, tt);
+          commit_prediction<G>(a, R, s, doit, b, k, pty, tt, is_cell, lane, gl);
         }
       } else {
         // Pass 1 — which (b,k) does the reference predict, and can the pair collide at all?
@@ -873,11 +1147,11 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
         // only possible event is an inner collision at rh: approaching and
         // rv^2 > vv (rr - rh^2) (if_coll :425-476).  A single-precision evaluation of the
         // same quantities with rigorous error margins rejects the pairs that certainly fail
-        // that test (receding, or missing by more than the margin); their slot is cleared
-        // here.  Everything else — local wells, bond pairs, hits and near misses — goes to
-        // the exact double-precision prediction of pass 2, compacted so that its lanes are
-        // all busy.  A rejected pair has no event in exact arithmetic either, so the table
-        // is bit-identical to predicting every candidate.
+        // that test (receding, or missing by more than the margin).  Everything else — local
+        // wells, bond pairs, hits and near misses — goes to the exact double-precision
+        // prediction of pass 2, compacted so that its lanes are all busy.  A rejected pair
+        // has no event in exact arithmetic either, so the table is bit-identical to
+        // predicting every candidate.
         // One lane per partner k; it is tested against both event beads, sharing its loads.
         // The two tests of a lane (partner k against bi and against bj) are the same
         // arithmetic on two data sets: they run as packed float2 operations (FFMA2 / FADD2
@@ -892,16 +1166,14 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
                      noz = make_float2(0.0f, -float(J.z - I.z));
         // lengths: |x_k(t_k) - x_b(t)| <= stretched chain + |v_k| dt; one more |v_k| dt for the
         // advance and one box for the wrap
-        const unsigned gshift = (threadIdx.x & 31u) & ~unsigned(G - 1);
-        const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
-        const unsigned below = (1u << lane) - 1u;
         const unsigned long long bm0 = __ldg(&R.bmask[bi]), bm1 = __ldg(&R.bmask[bj]);
         int cnt = 0;
         for (int base = 0; base < nb; base += G) {
           const int kk = base + lane;
           const bool kin = kk < nb;
           const int k = kin ? kk : 0;
-          const unsigned ck = BCELL(s, k);
+          const uint2 ckw = *reinterpret_cast<const uint2 *>(s.b + BSTRIDE * k + F_CELL);
+          const unsigned ck = ckw.x, own_k = ckw.y;
           const double2 *rk = reinterpret_cast<const double2 *>(s.b + BSTRIDE * k);
           const double2 k0 = rk[0], k1 = rk[1], k2 = rk[2];
           const float dtf = float(t - BT(s, k));
@@ -940,17 +1212,20 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
 #pragma unroll
           for (int q = 0; q < 2; q++) {
             const int b = q ? bj : bi;
-            const unsigned cb = q ? cb1 : cb0;
             const int d = abs(b - k);
-            // nb + pair index (k == b: some other valid slot, never stored)
-            const int slot = int(s.slot_row[min(b, k)]) + max(b, k);
-            const unsigned am = adj_mask(cb, ck, ncm1x3);
-            // which (b,k) the reference predicts at this event
-            const bool want_cell = d >= 3 && int((ck >> (8 * axis)) & 0xffu) == far &&
-                                   (am & others) == others;
-            const bool want_coll = d < 3 || (am & 0x00ffffffu) == 0x00ffffffu;
-            const bool active = has && kin && k != b && (q == 0 || !is_cell);
-            const bool doit = active && (is_cell ? want_cell : want_coll);
+            // which (b,k) the reference predicts at this event: local wells at a collision,
+            // nonlocal partners in the probed cells
+            bool want;
+            if (a.cell_masks) {
+              want = __popc((q ? probe1 : probe0) & own_k) == 3;
+            } else {
+              const unsigned am = adj_mask(q ? cb1 : cb0, ck, ncm1x3);
+              want = is_cell ? (int((ck >> (8 * axis)) & 0xffu) == far && (am & others) == others)
+                             : (am & 0x00ffffffu) == 0x00ffffffu;
+            }
+            // (bj's side: collisions only, and the pair (bi,bj) itself is bi's)
+            const bool active = has && kin && k != b && (q == 0 || (!is_cell && k != bi));
+            const bool doit = active && (d < 3 ? !is_cell : want);
             const bool plain = (((q ? bm1 : bm0) >> k) & 1ull) == 0ull; // no bond bookkeeping
             const bool far_apart = (q ? gap.y : gap.x) > far_min;
             const bool receding = (q ? rv.y : rv.x) > (q ? rv_min.y : rv_min.x);
@@ -965,12 +1240,9 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
 #else
             const bool keep = doit && !reject;
 #endif
-            // collision: every slot of bi / bj that is not (re)predicted is cleared (its
-            // latched type is only ever read for a slot that wins the argmin)
+            const unsigned gbits = gl.ballot(keep);
             // (branch-free: a store that is not wanted goes to the scratch slot)
-            s.evt[(active && !is_cell && !keep) ? slot : a.nslots] = CUDART_INF;
-            const unsigned gbits = (__ballot_sync(0xffffffffu, keep) >> gshift) & gmask;
-            const int dst = keep ? cnt + __popc(gbits & below) : 2 * nb;
+            const int dst = keep ? cnt + __popc(gbits & gl.below) : 2 * nb;
 #ifdef HMC_VERIFY_PREFILTER
             s.plist[dst] = uint8_t((k + q * nb) | (flagged ? 0x80 : 0));
 #else
@@ -995,18 +1267,15 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
           const int b = second ? bj : bi;
           const int k = on ? (second ? idx - nb : idx) : b;
           const int d = abs(b - k);
-          const int srow = int(s.slot_row[min(b, k)]) + max(b, k);
-          const int slot = k == b ? nb : srow; // an in-range dummy for an idle lane
+          const int pq = b * PINFO_STRIDE + k;
           double tt;
-          const unsigned pty =
-              predict_pair<SC>(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[slot - nb]), on, tt);
-          const bool have = on && pty != 0xffu;
+          unsigned pty = predict_pair<SC>(a, R, s, b, k, b < k, d, __ldg(&R.pinfo[pq]), on, tt);
 #ifdef HMC_VERIFY_PREFILTER
           // the pre-filter rejected a real event: flag it and record the first offender
           // (bits 8-13 b, 14-19 k, 20 crossing) for profiles/verify_prefilter.py
-          if (have && (raw & 0x80) && !(R.err & 0x40000000u)) {
+          if (on && pty != 0xffu && (raw & 0x80) && !(R.err & 0x40000000u)) {
             R.err |= 0x40000000u | (unsigned(b) << 8) | (unsigned(k) << 14) | (is_cell ? 1u << 20 : 0u);
-            if (R.tracing && R.live) { // dump the pair's state as records of type >= 200
+            if (R.flags == (REP_LIVE | REP_TRACING)) { // dump the pair's state as records of type >= 200
               unsigned n = *a.trace_n;
               auto put = [&](unsigned ty, double v) {
                 if (n < a.trace_cap) {
@@ -1030,17 +1299,14 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
             }
           }
 #endif
-          const double tnew = have ? tt : CUDART_INF;
-          // collision: overwrite (or clear) the slot; crossing: keep the earlier of old/new
-          const double told = s.evt[slot];
-          const bool store = on & (!is_cell | (have & (tnew < told)));
-          const int wslot = store ? slot : a.nslots; // scratch slot when nothing is to be written
-          s.evt[wslot] = tnew;
-          s.evty[wslot] = uint8_t(pty);
+          commit_prediction<G>(a, R, s, on, b, k, pty, tt, is_cell, lane, gl);
         }
       }
       __syncwarp();
     }
+    // drop what the collision invalidated and find the next event
+    next_event<G>(s, R, coll, bi, bj, n_old, lane, gl, bt_io, bk_io);
+    __syncwarp();
   }
 }
 
@@ -1061,7 +1327,7 @@ __device__ __forceinline__ void advance_all(const KArgs &a, const Smem &s, doubl
 // -------------------------------------------------------------- sampling --
 
 __device__ __forceinline__ void record_config_int(const KArgs &a, const Rep &R, int lane) {
-  if (a.cfg_cap && lane == 0 && R.live) {
+  if (a.cfg_cap && lane == 0 && rep_live(R)) {
     const unsigned n = a.cfg_n[R.r];
     if (n < a.cfg_cap) a.cfg_int[size_t(R.r) * a.cfg_cap + n] = R.config;
     a.cfg_n[R.r] = n + 1;
@@ -1071,10 +1337,12 @@ __device__ __forceinline__ void record_config_int(const KArgs &a, const Rep &R, 
 // body of run_trajectory after run_step, main.cc:199-225 (whole warp executes; only
 // groups with `on` sample; `step` may differ between the groups of a warp)
 template <int G>
-__device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step, double e0,
-                            int lane, bool on) {
+__device__ HMC_COLD unsigned sample_step(const KArgs &a, const Rep &R_in, const Smem &s_in,
+                                             unsigned step, double e0, int lane, bool on) {
+  Rep R = R_in;
+  const Smem s = s_in;
   const int trans = R.r / a.replicas_per_trans;
-  const bool out = on && R.live; // global side effects
+  const bool out = on && rep_live(R); // global side effects
   // dist_between_nonlocal_beads (hardspheres.cc:1084-1104)
   if (a.dist_cap || a.hist_bins) {
     const unsigned nrow = (a.dist_cap && out) ? a.dist_n[R.r] : 0u;
@@ -1082,7 +1350,7 @@ __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step
     // split tools/mfpt.py applies to the dist rows (mfpt.py:104-125)
     int st_on = 0;
     if (a.hist_bins && R.tr->n_transient)
-      st_on = dist2_ij(a, s.b + F_X, R.tr->tb_i[0], R.tr->tb_j[0]) < R.rc2 ? 1 : 0;
+      st_on = dist2_ij(a, s.b + F_X, R.tr->tb_i[0], R.tr->tb_j[0]) < R.tr->rc2 ? 1 : 0;
     for (int k = lane; k < int(R.tr->n_nonlocal) && out; k += G) {
       const int i = R.tr->nl_i[k], j = R.tr->nl_j[k];
       const double d = sqrt(dist2_ij(a, s.b + F_X, i, j));
@@ -1102,12 +1370,12 @@ __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step
   }
   const bool rec = on && (step % a.write_step == 0);
   if (rec) {
-    if (lane == 0 && R.live && R.config < (unsigned long long)a.nstates)
+    if (lane == 0 && rep_live(R) && R.config < (unsigned long long)a.nstates)
       atomicAdd(&a.acc[size_t(trans) * a.nstates + R.config], 1ull);
     record_config_int(a, R, lane);
   }
   // unique_config: first recorded sample with config == 1 (main.cc:211-216)
-  const bool take = rec && R.live && R.config == 1ull && !a.uniq_found[R.r];
+  const bool take = rec && rep_live(R) && R.config == 1ull && !a.uniq_found[R.r];
   __syncwarp();
   if (take) {
     for (int k = lane; k < a.nb; k += G) {
@@ -1126,6 +1394,7 @@ __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step
   const double e1 = hamiltonian(a, R, s);
   const double ediff = fabs(1 - (e1 / e0));
   if (on && !(ediff < 1e-6)) R.err |= HMC_ERR_ENERGY;
+  return R.err;
 }
 
 // ------------------------------------------------------------- crankshaft --
@@ -1134,14 +1403,22 @@ __device__ void sample_step(const KArgs &a, Rep &R, const Smem &s, unsigned step
 // bond (ind-1, ind), geometric checks, trial bitmask, Metropolis on s_bias.
 // Trial coordinates use the velocity arrays as scratch (velocities are redrawn at the
 // start of every MD step; they are saved to global memory before the first move).
+struct CrankOut {
+  unsigned long long config;
+  unsigned err, words, moves_done;
+};
 template <int G>
-__device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &ws,
-                            unsigned move_offset, unsigned n_moves, int lane, unsigned gmask,
-                            bool on) {
+__device__ HMC_COLD CrankOut crank_moves(const KArgs &a, const Rep &R_in, const Smem &s_in,
+                                             const WordStream &ws_in, unsigned move_offset,
+                                             unsigned n_moves, int lane, unsigned gmask, bool on) {
+  Rep R = R_in;
+  const Smem s = s_in;
+  WordStream ws = ws_in;
   const int nb = a.nb;
   // dead: this group sits the moves out (it is not at a crankshaft point of its
   // schedule, or its tape ran out)
-  bool dead = !on;
+  bool dead = !on, stuck = false;
+  unsigned long long n_att = 0, n_acc = 0;
   for (unsigned mv = 0; mv < n_moves; mv++) {
     const unsigned start = ws.c;
     unsigned attempts = 0;
@@ -1149,6 +1426,14 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
     // retry loop of crankshaft.cc:245-253; warp-uniform: groups that already hold a
     // valid trial are predicated off until every group of the warp has one
     for (;;) {
+      // (the reference's loop is unbounded, crankshaft.cc:245-253: a rotation keeps every
+      // nearest / next-nearest distance, so a chain with a local bond marginally outside
+      // its well fails the strict check on every trial.  One such replica would hang the
+      // whole persistent launch, so the search is capped and the replica flagged.)
+      if (!ok && !dead && attempts >= (1u << 20)) {
+        dead = true;
+        stuck = true;
+      }
       const bool need = !ok && !dead;
       if (!warp_any<G>(need)) break;
       unsigned ind = 1;
@@ -1221,7 +1506,7 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
     if (dead) {
       if (ws.c != start) { // roll the unfinished move back (positions untouched)
         ws.c = start;
-        R.err |= HMC_ERR_TAPE_UNDERRUN;
+        R.err |= stuck ? HMC_ERR_CRANK_STUCK : HMC_ERR_TAPE_UNDERRUN;
       }
     } else {
       // config_int, crankshaft.cc:175-205: only transient-bond pairs can set bits
@@ -1232,10 +1517,10 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
         bool first = true;
         for (unsigned q = 0; q < k; q++)
           if (R.tr->tb_i[q] == i && R.tr->tb_j[q] == j) first = false;
-        if (first && !(d2 > R.rc2)) trial ^= (1ull << k);
+        if (first && !(d2 > R.tr->rc2)) trial ^= (1ull << k);
       }
       // accept_move, crankshaft.cc:207-222
-      const double dS = R.sb[trial] - R.sb[R.config];
+      const double dS = rep_sbias(a, R)[trial] - rep_sbias(a, R)[R.config];
       accept = true;
       if (dS > 0) {
         const unsigned w0 = ws_next(ws), w1 = ws_next(ws);
@@ -1250,7 +1535,7 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
         }
       }
     }
-    if (!dead) R.n_att += attempts;
+    if (!dead) n_att += attempts;
     __syncwarp();
     if (accept) {
       for (int k = lane; k < nb; k += G) {
@@ -1259,17 +1544,28 @@ __device__ void crank_moves(const KArgs &a, Rep &R, const Smem &s, WordStream &w
         BZ(s, k) = BVZ(s, k);
       }
       R.config = trial;
-      R.n_acc++;
+      n_acc++;
     }
     __syncwarp();
     // main.cc:232-236
     if (!dead) {
-      R.moves_done++;
+      ws.moves_done++;
       const unsigned i = move_offset + mv;
       for (unsigned j = 1; j < a.mc_write; j++)
         if (i == (j * a.mc_moves) / a.mc_write) record_config_int(a, R, lane);
     }
   }
+  if (lane == 0 && rep_live(R)) {
+    unsigned long long *ev = a.acc + size_t(a.n_trans) * a.nstates + 2 * size_t(a.n_trans);
+    if (n_att) atomicAdd(&ev[2], n_att);
+    if (n_acc) atomicAdd(&ev[3], n_acc);
+  }
+  CrankOut out;
+  out.config = R.config;
+  out.err = R.err;
+  out.words = ws.c;
+  out.moves_done = ws.moves_done;
+  return out;
 }
 
 // -------------------------------------------------------------- the kernel --
@@ -1278,26 +1574,26 @@ __device__ __forceinline__ double wl_gamma(const KArgs &a, unsigned iter_wl) {
   return iter_wl == 0 ? a.gamma0 : 1.0 / double(iter_wl); // main.cc:283,302-303
 }
 
-template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hmc_ensemble_kernel(const __grid_constant__ KArgs a) {
+template <int G, bool SC, bool TP>
+__global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hmc_ensemble_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & (G - 1);
-  const unsigned gmask = group_mask<G>();
-  const int group_in_cta = threadIdx.x / G;
+  // (read once through an opaque asm: under register pressure the compiler otherwise
+  // re-reads the special register — an S2R with its latency — at every use)
+  unsigned tid;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+  const int lane = int(tid & unsigned(G - 1));
+  const unsigned wlane = tid & 31u;
+  const unsigned gmask = group_mask<G>(wlane);
+  const GroupLanes<G> gl(lane, wlane);
+  const int group_in_cta = int(tid / unsigned(G));
   const int nb = a.nb;
-  // CTA-shared row offsets of the triangular pair table, behind the replica images:
-  // slot(lo,hi) = nb + pair_index(lo,hi) = slot_row[lo] + hi
-  uint16_t *slot_row =
-      reinterpret_cast<uint16_t *>(smem_raw + size_t(blockDim.x / G) * a.smem_per_replica);
-  for (int q = threadIdx.x; q < nb; q += blockDim.x)
-    slot_row[q] = uint16_t(nb + q * (2 * nb - q - 1) / 2 - q - 1);
-  __syncthreads();
-  const Smem s = carve(smem_raw + size_t(group_in_cta) * a.smem_per_replica, slot_row, nb, a.nslots);
+  const Smem s = carve(smem_raw + size_t(group_in_cta) * a.smem_per_replica, a);
 
   constexpr int NG = 32 / G; // replica groups per warp, run in lockstep
-  const int group_in_warp = (threadIdx.x & 31) / G;
+  const int group_in_warp = int(wlane) / G;
   for (;;) {
     int r0 = 0;
-    if ((threadIdx.x & 31) == 0) r0 = int(atomicAdd(a.work_counter, unsigned(NG)));
+    if (wlane == 0) r0 = int(atomicAdd(a.work_counter, unsigned(NG)));
     r0 = __shfl_sync(0xffffffffu, r0, 0);
     if (r0 >= a.n_replicas) break;
     // a group past the end of the ensemble runs a clone of the last replica with all
@@ -1308,22 +1604,16 @@ template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_B
     Rep R;
     R.r = r;
     const int trans = r / a.replicas_per_trans;
+    R.trans = trans;
     R.tr = a.trans + trans;
-    R.pinfo = a.pairinfo + size_t(trans) * a.npairs;
+    R.pinfo = a.pairinfo + size_t(trans) * size_t(a.nb) * PINFO_STRIDE;
     R.bmask = a.bondmask + size_t(trans) * a.nb;
-    R.sb = a.s_bias + size_t(r) * a.nstates;
     R.config = a.config[r];
-    R.rc2 = R.tr->rc2;
-    R.stair2 = R.tr->stair2;
-    R.p_rc2 = R.tr->p_rc2;
-    R.has_stair = R.tr->has_stair;
-    R.has_p_rc = R.tr->has_p_rc;
-    R.max_nbonds = R.tr->max_nbonds;
     R.err = 0;
-    R.n_coll = R.n_cell = R.n_att = R.n_acc = R.formed = R.broken = 0;
-    R.moves_done = 0;
-    R.tracing = (a.trace_cap != 0 && a.trace_replica == r);
-    R.live = live;
+    R.n_coll = R.n_cell = 0;
+    R.nl = 0;
+    R.flags = (live ? REP_LIVE : 0u) |
+              ((a.trace_cap != 0 && a.trace_replica == r) ? REP_TRACING : 0u);
 
     // load the replica (bead clocks all equal t_now at a step boundary)
     for (int k = lane; k < nb; k += G) {
@@ -1339,16 +1629,30 @@ template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_B
     }
     __syncwarp();
 
-    WordStream ws;
-    ws.tape = a.tape_words ? a.tape_words + size_t(r) * a.tape_n : nullptr;
-    ws.n = a.tape_n;
-    ws.c = 0;
-    ws.underrun = false;
-    ws.philox = (a.rng_mode == HMC_RNG_PHILOX);
-    ws.key = make_uint2(a.seed0, a.seed1);
-    ws.c1 = ws.c2 = 0;
-    ws.c3 = unsigned(r);
-    ws.buf_blk = 0xffffffffu;
+    // crankshaft word source (built where it is used: it is not live across the event loop)
+    auto make_ws = [&]() {
+      WordStream ws;
+      ws.tape = a.tape_words ? a.tape_words + size_t(r) * a.tape_n : nullptr;
+      ws.n = a.tape_n;
+      ws.c = 0;
+      ws.underrun = false;
+      ws.philox = (a.rng_mode == HMC_RNG_PHILOX);
+      ws.key = make_uint2(a.seed0, a.seed1);
+      ws.c1 = ws.c2 = 0;
+      ws.c3 = unsigned(r);
+      ws.buf_blk = 0xffffffffu;
+      ws.moves_done = 0;
+      return ws;
+    };
+    // valid events of the finished interval -> global counters
+    auto flush_events = [&]() {
+      if (lane == 0 && live) {
+        unsigned long long *ev = a.acc + size_t(a.n_trans) * a.nstates + 2 * size_t(a.n_trans);
+        if (R.n_coll) atomicAdd(&ev[0], (unsigned long long)R.n_coll);
+        if (R.n_cell) atomicAdd(&ev[1], (unsigned long long)R.n_cell);
+      }
+      R.n_coll = R.n_cell = 0;
+    };
 
     bool vel_dirty = false; // velocity arrays hold crankshaft scratch
     auto save_vel = [&](bool on) {
@@ -1364,11 +1668,16 @@ template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_B
     };
 
     if (a.op == HMC_OP_CRANK_ONLY) {
-      crank_moves<G>(a, R, s, ws, a.move_offset, a.count, lane, gmask, true);
+      const WordStream wc = make_ws();
+      const Rep Rc = R;
+      const Smem sc = s;
+      const CrankOut co = crank_moves<G>(a, Rc, sc, wc, a.move_offset, a.count, lane, gmask, true);
+      R.config = co.config;
+      R.err = co.err;
       vel_dirty = true;
       if (lane == 0 && live && a.tape_consumed) {
-        a.tape_consumed[r] = ws.c;
-        a.tape_consumed[a.n_replicas + r] = R.moves_done;
+        a.tape_consumed[r] = co.words;
+        a.tape_consumed[a.n_replicas + r] = co.moves_done;
       }
     } else {
       // ---- the replica's schedule as a flat list of event steps e = 0 .. E-1 ----
@@ -1388,7 +1697,8 @@ template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_B
       bool in_step = false;
       double step_time = 0.0, e0 = 0.0;
       unsigned cur_st = 0;
-      unsigned guard = 0;
+      double bt = CUDART_INF; // next event of the replica (carried from event to event)
+      unsigned bk = 0u;
       for (;;) {
         // -- start the next step --
         const bool start = !in_step && e < E;
@@ -1407,7 +1717,14 @@ template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_B
             const double *nrm =
                 (a.normals && do_init) ? a.normals + (size_t(r) * nunits + ninit) * size_t(nb) * 3
                                        : nullptr;
-            init_step<G, SC>(a, R, s, nrm, a.md_draw_base + ninit, lane, gmask, do_init);
+            // (the callee gets COPIES: if the address of R or s themselves escaped into a call
+            // they could no longer live in registers during the event loop)
+            const Rep Rc = R;
+            const Smem sc = s;
+            const StepOut so =
+                init_step<G, SC>(a, Rc, sc, nrm, a.md_draw_base + ninit, lane, wlane, gmask, do_init);
+            R.err = so.err;
+            R.nl = so.nl;
             const double h0 = hamiltonian(a, R, s);
             if (do_init) {
               e0 = h0;
@@ -1418,25 +1735,27 @@ template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_B
             cur_st = st;
             step_time = double(st) * (wl ? a.del_t_wl : a.del_t);
             in_step = true;
-            guard = 0;
           }
+          // first event of the step (for the groups in the middle of a step this recomputes
+          // what they carry: their tables have not changed)
+          next_event<G>(s, R, false, 0, 0, 0, lane, gl, bt, bk);
         }
         // -- next event of the current step --
-        double bt;
-        int bs;
-        table_argmin<G>(s, a.nslots, lane, bt, bs);
         // a step of the shipped configurations has 5e2-1e4 events; a runaway replica
         // (non-finite state) is flagged and its step cut short instead of hanging
-        const bool overrun = in_step && ++guard > a.max_events_per_step;
+        const bool overrun = in_step && (R.n_coll + R.n_cell) >= a.max_events_per_step;
         if (overrun) R.err |= HMC_ERR_NAN;
         const bool has = in_step && (bt <= step_time) && !overrun;
         // -- finish the step --
         const bool finish = in_step && !has;
         if (warp_any<G>(finish)) {
           advance_all<G>(a, s, step_time, lane, finish);
+          if (finish) flush_events();
           const unsigned unit = e / per, sub = e - unit * per;
           if (a.phase == HMC_PHASE_MAIN) {
-            sample_step<G>(a, R, s, cur_st, e0, lane, finish);
+            const Rep Rc = R;
+            const Smem sc = s;
+            R.err = sample_step<G>(a, Rc, sc, cur_st, e0, lane, finish);
           } else if (wl) {
             const double e1 = hamiltonian(a, R, s);
             if (finish && !(fabs(1 - (e1 / e0)) < 1e-6)) R.err |= HMC_ERR_ENERGY;
@@ -1445,8 +1764,9 @@ template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_B
               const unsigned iter_wl = a.op == HMC_OP_RUN ? a.first + unit / unsigned(a.nstates)
                                                           : (a.first + unit) / unsigned(a.nstates);
               const double g = wl_gamma(a, iter_wl);
-              if (R.config == 0ull) R.sb[a.nstates - 1] -= g;
-              else R.sb[a.nstates - 1] += g;
+              double *sb = rep_sbias(a, R);
+              if (R.config == 0ull) sb[a.nstates - 1] -= g;
+              else sb[a.nstates - 1] += g;
             }
             __syncwarp();
           }
@@ -1455,15 +1775,18 @@ template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_B
                              a.mc_moves != 0 && sub + 1 == per;
           if (warp_any<G>(crank)) {
             save_vel(crank);
+            WordStream wc = make_ws();
             if (crank) {
               const unsigned long long mcd = a.mc_draw_base + unit;
-              ws.c = 0;
-              ws.c1 = unsigned(mcd);
-              ws.c2 = unsigned(mcd >> 32) | 0x80000000u;
-              ws.buf_blk = 0xffffffffu;
+              wc.c1 = unsigned(mcd);
+              wc.c2 = unsigned(mcd >> 32) | 0x80000000u;
               vel_dirty = true;
             }
-            crank_moves<G>(a, R, s, ws, 0u, a.mc_moves, lane, gmask, crank);
+            const Rep Rc = R;
+            const Smem sc = s;
+            const CrankOut co = crank_moves<G>(a, Rc, sc, wc, 0u, a.mc_moves, lane, gmask, crank);
+            R.config = co.config;
+            R.err = co.err;
           }
           if (finish) {
             in_step = false;
@@ -1475,7 +1798,7 @@ template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_B
           if (!warp_any<G>(in_step || e < E)) break;
           continue;
         }
-        event_body<G, SC>(a, R, s, has, bt, bs, lane);
+        event_body<G, SC, TP>(a, R, s, has, bt, bk, lane, gl);
       }
     }
 
@@ -1490,17 +1813,10 @@ template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_B
       }
     }
     save_vel(!vel_dirty);
+    flush_events();
     if (lane == 0 && live) {
       a.config[r] = R.config;
       if (R.err) atomicOr(&a.err[r], R.err);
-      const size_t base = size_t(a.n_trans) * a.nstates;
-      if (R.formed) atomicAdd(&a.acc[base + trans], R.formed);
-      if (R.broken) atomicAdd(&a.acc[base + a.n_trans + trans], R.broken);
-      unsigned long long *ev = a.acc + base + 2 * size_t(a.n_trans);
-      if (R.n_coll) atomicAdd(&ev[0], R.n_coll);
-      if (R.n_cell) atomicAdd(&ev[1], R.n_cell);
-      if (R.n_att) atomicAdd(&ev[2], R.n_att);
-      if (R.n_acc) atomicAdd(&ev[3], R.n_acc);
     }
     __syncwarp();
   }
@@ -1510,24 +1826,70 @@ template <int G, bool SC> __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_B
 
 // ---------------------------------------------------------------- launcher --
 
-size_t hmc_smem_per_replica(int nb) {
-  const size_t npairs = size_t(nb) * (nb - 1) / 2;
-  const size_t nslots = nb + npairs;
-  size_t bytes = 8 * (size_t(BSTRIDE) * nb + nslots + 1) + (nslots + 1) + 2 * size_t(nb) + 1;
-  return (bytes + 15) & ~size_t(15);
+int hmc_pick_group(int nb);
+
+// bytes of a replica image besides the event list
+static size_t smem_fixed(int nb) { return 8 * size_t(BSTRIDE) * nb + 8 * size_t(nb) + 2 * size_t(nb) + 1 + 32; }
+
+int hmc_list_capacity(int nb, int group) {
+  // Live nonlocal predictions per replica: ~0.5 nb on average; the list transiently also
+  // holds the predictions of the running event.  Peaks measured on the CPU (2e5-event
+  // probes): 1.5 nb for 46-50 beads, 2.4 nb for 20 beads with permanent bonds, with a slowly
+  // decaying tail (20 beads overflowed 64 entries once in 1e9 events).  Wanted:
+  // max(3.5 nb, 96); at least 3 nb; in between, whatever keeps 16 warps per SM resident.
+  // An overflow raises HMC_ERR_LIST_OVERFLOW.  A multiple of 8.
+  const int nonlocal = nb >= 4 ? (nb - 3) * (nb - 2) / 2 : 0;
+  int want = (7 * nb + 1) / 2;
+  if (want < 96) want = 96;
+  int cap = want;
+  if (const char *e = getenv("HMC_LIST_CAP")) { // tuning / test knob
+    const int v = atoi(e);
+    if (v > 0) cap = want = v;
+  } else {
+    const long long replicas = 16ll * (32 / group);               // per SM at 16 warps
+    const long long budget = (233472ll - 4 * (1024 + 512)) / replicas; // bytes per replica
+    const long long fit = (budget - (long long)smem_fixed(nb)) / 16;
+    if (fit < cap) cap = int(fit > 3 * nb ? fit : 3 * nb);
+    if (cap > want) cap = want;
+  }
+  // (every nonlocal pair live plus the predictions of one event: more cannot be in the list)
+  if (cap > nonlocal + 2 * nb) cap = nonlocal + 2 * nb;
+  if (cap < 8) cap = 8;
+  return (cap + 7) & ~7;
+}
+
+// byte offsets of the arrays inside a replica image (see Smem)
+void hmc_smem_layout(int nb, int group, uint32_t *off_tnn, uint32_t *off_list, uint32_t *off_plist,
+                     uint32_t *total) {
+  const size_t cap = size_t(hmc_list_capacity(nb, group));
+  const size_t tnn = 8 * size_t(BSTRIDE) * nb;   // bead records are 80 B: 16-byte aligned
+  size_t list = tnn + 8 * size_t(nb);
+  list = (list + 15) & ~size_t(15);               // 16-byte entries
+  const size_t plist = list + 16 * cap;
+  const size_t bytes = (plist + 2 * size_t(nb) + 1 + 15) & ~size_t(15);
+  if (off_tnn) *off_tnn = uint32_t(tnn);
+  if (off_list) *off_list = uint32_t(list);
+  if (off_plist) *off_plist = uint32_t(plist);
+  if (total) *total = uint32_t(bytes);
+}
+
+size_t hmc_smem_per_replica(int nb, int group) {
+  uint32_t total = 0;
+  hmc_smem_layout(nb, group, nullptr, nullptr, nullptr, &total);
+  return total;
 }
 
 int hmc_pick_group(int nb) {
-  // lanes per replica (measured on B200, profiles/README.md): the per-event work that
-  // every lane of a group repeats (argmin reduce, collision arithmetic, cell walls) is
-  // shared by 32/G replicas per warp, so small chains want narrow groups; from ~32
-  // beads on the partner loop dominates and a full warp per replica wins.
+  // lanes per replica: the per-event work that every lane of a group repeats (event
+  // arithmetic, cell walls, the reduce of the argmin) is shared by the 32/G replicas of a
+  // warp, so narrow groups win as long as the partner loops keep their lanes busy and the
+  // replica images of 16 warps fit in shared memory: 8 lanes up to 24 beads, 16 beyond
+  // (46 beads: 6.4 KB per replica, 32 replicas per SM).
   if (nb <= 24) return 8;
-  if (nb <= 32) return 16;
-  return 32;
+  return 16;
 }
 
-template <int G, bool SC>
+template <int G, bool SC, bool TP>
 static cudaError_t launch_g(const KArgs &a, cudaStream_t stream, int *grid_out, int *block_out) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -1538,16 +1900,16 @@ static cudaError_t launch_g(const KArgs &a, cudaStream_t stream, int *grid_out, 
   size_t smem = 0;
   int best_warps = -1;
   for (int cand = HMC_BLOCK; cand >= 64 && cand >= G; cand /= 2) {
-    const size_t sm = size_t(cand / G) * a.smem_per_replica +
-                      ((size_t(a.nb) * sizeof(uint16_t) + 15) & ~size_t(15));
-    cudaError_t e = cudaFuncSetAttribute(hmc_ensemble_kernel<G, SC>,
+    // (+512: the list scans read whole lane strides, up to 31 entries past the capacity)
+    const size_t sm = size_t(cand / G) * a.smem_per_replica + 512;
+    cudaError_t e = cudaFuncSetAttribute(hmc_ensemble_kernel<G, SC, TP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));
     if (e != cudaSuccess) {
       cudaGetLastError();
       continue;
     }
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, hmc_ensemble_kernel<G, SC>, cand, sm);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, hmc_ensemble_kernel<G, SC, TP>, cand, sm);
     if (e != cudaSuccess) {
       cudaGetLastError();
       continue;
@@ -1560,34 +1922,41 @@ static cudaError_t launch_g(const KArgs &a, cudaStream_t stream, int *grid_out, 
     }
   }
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(hmc_ensemble_kernel<G, SC>,
+  cudaError_t e = cudaFuncSetAttribute(hmc_ensemble_kernel<G, SC, TP>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
+  // persistent grid: every resident warp slot, never more CTAs than work.  (Warps pull
+  // batches of 32/G replicas and keep each for its whole schedule.  Measured: spreading the
+  // batches over fewer, equally loaded warps is slower — a warp's pace hardly depends on how
+  // many share its SM, so only the number of rounds counts.)
   const int groups_per_cta = block / G;
-  // persistent grid: a multiple of the SM count, never more CTAs than work
   long long need = (a.n_replicas + groups_per_cta - 1) / groups_per_cta;
   long long grid = (long long)sms * per_sm;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  hmc_ensemble_kernel<G, SC><<<int(grid), block, smem, stream>>>(a);
+  hmc_ensemble_kernel<G, SC, TP><<<int(grid), block, smem, stream>>>(a);
   if (grid_out) *grid_out = int(grid);
   if (block_out) *block_out = block;
   return cudaGetLastError();
 }
 
+template <bool SC>
+static cudaError_t launch_sc(const KArgs &a, int group, cudaStream_t stream, int *grid_out,
+                             int *block_out) {
+  // TP: partner re-prediction as pre-filter + compacted exact pass (chains >= 16 beads)
+  if (!a.two_pass)
+    return group == 8 ? launch_g<8, SC, false>(a, stream, grid_out, block_out)
+                      : launch_g<16, SC, false>(a, stream, grid_out, block_out);
+  switch (group) {
+  case 8: return launch_g<8, SC, true>(a, stream, grid_out, block_out);
+  case 32: return launch_g<32, SC, true>(a, stream, grid_out, block_out);
+  default: return launch_g<16, SC, true>(a, stream, grid_out, block_out);
+  }
+}
+
 cudaError_t hmc_launch(const KArgs &a, int group, cudaStream_t stream, int *grid_out,
                        int *block_out) {
   // SC: min-image fast path for chains shorter than 1.5 boxes, chosen per launch
-  if (a.short_chain) {
-    switch (group) {
-    case 8: return launch_g<8, true>(a, stream, grid_out, block_out);
-    case 16: return launch_g<16, true>(a, stream, grid_out, block_out);
-    default: return launch_g<32, true>(a, stream, grid_out, block_out);
-    }
-  }
-  switch (group) {
-  case 8: return launch_g<8, false>(a, stream, grid_out, block_out);
-  case 16: return launch_g<16, false>(a, stream, grid_out, block_out);
-  default: return launch_g<32, false>(a, stream, grid_out, block_out);
-  }
+  return a.short_chain ? launch_sc<true>(a, group, stream, grid_out, block_out)
+                       : launch_sc<false>(a, group, stream, grid_out, block_out);
 }

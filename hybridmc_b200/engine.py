@@ -16,6 +16,7 @@ PHASE_EQ, PHASE_WL, PHASE_MAIN = 0, 1, 2
 
 ERR_LOCAL_OVERLAP, ERR_NONLOCAL_OVERLAP, ERR_ENERGY = 1, 2, 4
 ERR_NAN, ERR_TAPE_UNDERRUN, ERR_SAMPLE_OVERFLOW = 8, 16, 32
+ERR_LIST_OVERFLOW, ERR_CRANK_STUCK = 64, 128
 
 EVENT_DTYPE = np.dtype([("t", "<f8"), ("type", "<u4"), ("i", "<u4"), ("j", "<u4"),
                         ("pad", "<u4")])

@@ -101,7 +101,11 @@ enum hmc_error_flag {
   HMC_ERR_ENERGY = 4,           /* main.cc:219-225 "energy is not conserved" */
   HMC_ERR_NAN = 8,              /* non-finite event time */
   HMC_ERR_TAPE_UNDERRUN = 16,   /* injected crankshaft tape exhausted */
-  HMC_ERR_SAMPLE_OVERFLOW = 32  /* optional sample buffer full (samples dropped) */
+  HMC_ERR_SAMPLE_OVERFLOW = 32, /* optional sample buffer full (samples dropped) */
+  HMC_ERR_LIST_OVERFLOW = 64,   /* more live nonlocal predictions than the event list holds
+                                   (HMC_LIST_CAP raises the capacity); the replica's
+                                   trajectory is no longer the reference's */
+  HMC_ERR_CRANK_STUCK = 128     /* a crankshaft move found no valid rotation in 2^20 trials */
 };
 
 typedef struct hmc_engine *hmc_handle;
