@@ -18,7 +18,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhybridmc_b200.so")
-SOURCES = ["hmc_kernels.cu", "hmc_api.cu", "hmc_host.cu", "hmc_program.cu", "hmc_h5.cu"]
+SOURCES = ["hmc_kernels.cu", "hmc_api.cu", "hmc_host.cu", "hmc_program.cu", "hmc_h5.cu", "hmc_comm.cu"]
 HEADERS = [os.path.join(CSRC, "hmc_internal.h"), os.path.join(CSRC, "host", "h5lite.h"),
            os.path.join(os.path.dirname(HERE), "include", "hybridmc_b200.h")]
 
@@ -49,7 +49,7 @@ def build_library(force=False, verbose=False, out=None, defines=()):
         return LIB
     cmd = [nvcc_path(), *nvcc_flags(["-D" + d for d in defines]), "-shared", "-o", out or LIB,
            *[os.path.join(CSRC, s) for s in SOURCES],
-           "-cudart", "static", "-Xlinker", "-l:libstdc++.so.6"]
+           "-cudart", "static", "-Xlinker", "-l:libstdc++.so.6", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#define HMC_ABI_VERSION 1
+#define HMC_ABI_VERSION 2
 
 namespace {
 thread_local std::string g_create_error;
@@ -42,6 +42,10 @@ struct hmc_engine {
   uint32_t *d_err = nullptr;
   unsigned long long *d_acc = nullptr;
   size_t n_acc = 0;
+  unsigned long long *d_acc_rep = nullptr; // per-replica counts (independent-program mode)
+  uint8_t *d_skip = nullptr;
+  bool skip_on = false;
+  uint32_t rng_first = 0, rng_total = 0;
   double *d_dist = nullptr;
   uint32_t *d_dist_n = nullptr;
   uint32_t dist_cap = 0;
@@ -172,6 +176,10 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.s_bias = h->d_sbias;
   a.err = h->d_err;
   a.acc = h->d_acc;
+  a.acc_rep = h->d_acc_rep;
+  a.skip = h->skip_on ? h->d_skip : nullptr;
+  a.rng_first = h->rng_first;
+  a.rng_total = h->rng_total ? h->rng_total : uint32_t(h->Rper);
   a.n_trans = h->T;
   a.dist = h->d_dist;
   a.dist_n = h->d_dist_n;
@@ -458,7 +466,8 @@ int hmc_destroy(hmc_handle h) {
                   h->d_sbias,    h->d_config,    h->d_err,        h->d_acc,        h->d_dist,
                   h->d_dist_n,   h->d_cfg_int,   h->d_cfg_n,      h->d_hist,       h->d_uniq_pos,
                   h->d_uniq_vel, h->d_uniq_found, h->d_trace,     h->d_trace_n,    h->d_work,
-                  h->d_normals,  h->d_tape_words, h->d_tape_consumed, h->d_tape_sin, h->d_tape_cos};
+                  h->d_normals,  h->d_tape_words, h->d_tape_consumed, h->d_tape_sin, h->d_tape_cos,
+                  h->d_acc_rep,  h->d_skip};
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -573,6 +582,9 @@ int hmc_reset_counts(hmc_handle h) {
   // config_count only; formed/broken/events keep accumulating like CountBond does
   CK(cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * size_t(h->T) * h->nstates,
                      h->stream));
+  if (h->d_acc_rep)
+    CK(cudaMemsetAsync(h->d_acc_rep, 0, sizeof(unsigned long long) * size_t(h->R) * h->nstates,
+                       h->stream));
   if (h->d_dist_n) CK(cudaMemsetAsync(h->d_dist_n, 0, sizeof(uint32_t) * h->R, h->stream));
   if (h->d_cfg_n) CK(cudaMemsetAsync(h->d_cfg_n, 0, sizeof(uint32_t) * h->R, h->stream));
   // distance histograms keep accumulating over rounds, like the reference's `dist`
@@ -748,6 +760,80 @@ int hmc_get_counts(hmc_handle h, uint64_t *config_count, int nstates, uint64_t *
     if (formed) formed[t] = acc[base + t];
     if (broken) broken[t] = acc[base + h->T + t];
   }
+  return 0;
+}
+
+int hmc_set_replica_ids(hmc_handle h, unsigned first, unsigned total_per_transition) {
+  if (!h) return fail(h, "null handle");
+  if (total_per_transition && first + unsigned(h->Rper) > total_per_transition)
+    return fail(h, "hmc_set_replica_ids: first + replicas_per_transition exceeds the total");
+  h->rng_first = first;
+  h->rng_total = total_per_transition;
+  return 0;
+}
+
+int hmc_enable_replica_counts(hmc_handle h, int on) {
+  if (!h) return fail(h, "null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (on && !h->d_acc_rep) {
+    CK(dalloc(&h->d_acc_rep, size_t(h->R) * h->nstates));
+  } else if (!on && h->d_acc_rep) {
+    cudaFree(h->d_acc_rep);
+    h->d_acc_rep = nullptr;
+  }
+  return 0;
+}
+
+int hmc_get_replica_counts(hmc_handle h, uint64_t *config_count) {
+  if (!h || !config_count) return fail(h, "hmc_get_replica_counts: null");
+  if (!h->d_acc_rep) return fail(h, "hmc_get_replica_counts: not enabled");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(config_count, h->d_acc_rep, sizeof(uint64_t) * size_t(h->R) * h->nstates,
+                     cudaMemcpyDeviceToHost, h->stream));
+  return sync(h);
+}
+
+int hmc_set_replica_skip(hmc_handle h, const uint8_t *skip) {
+  if (!h) return fail(h, "null handle");
+  CK(cudaSetDevice(h->device));
+  if (!skip) {
+    h->skip_on = false;
+    return 0;
+  }
+  if (!h->d_skip) CK(dalloc(&h->d_skip, size_t(h->R)));
+  CK(cudaMemcpyAsync(h->d_skip, skip, size_t(h->R), cudaMemcpyHostToDevice, h->stream));
+  h->skip_on = true;
+  return sync(h);
+}
+
+int hmc_allreduce_counts(hmc_handle h, hmc_comm c) {
+  if (!h) return fail(h, "null handle");
+  if (!c || hmc_comm_world(c) == 1) return 0;
+  CK(cudaSetDevice(h->device));
+  if (hmc_comm_allreduce_device_u64(c, h->d_acc, uint64_t(h->T) * h->nstates, h->stream) != 0)
+    return fail(h, std::string("hmc_allreduce_counts: ") + hmc_last_error(nullptr), -7);
+  return 0;
+}
+
+int hmc_allreduce_totals(hmc_handle h, hmc_comm c) {
+  if (!h) return fail(h, "null handle");
+  if (!c || hmc_comm_world(c) == 1) return 0;
+  CK(cudaSetDevice(h->device));
+  const uint64_t off = uint64_t(h->T) * h->nstates;
+  if (hmc_comm_allreduce_device_u64(c, h->d_acc + off, h->n_acc - off, h->stream) != 0)
+    return fail(h, std::string("hmc_allreduce_totals: ") + hmc_last_error(nullptr), -7);
+  return 0;
+}
+
+int hmc_allreduce_hist(hmc_handle h, hmc_comm c) {
+  if (!h) return fail(h, "null handle");
+  if (!h->d_hist) return fail(h, "hmc_allreduce_hist: histograms are not enabled");
+  if (!c || hmc_comm_world(c) == 1) return 0;
+  CK(cudaSetDevice(h->device));
+  const uint64_t n = uint64_t(h->T) * (h->n_nonlocal_max ? h->n_nonlocal_max : 1) * 2 * h->hist_bins;
+  if (hmc_comm_allreduce_device_u64(c, h->d_hist, n, h->stream) != 0)
+    return fail(h, std::string("hmc_allreduce_hist: ") + hmc_last_error(nullptr), -7);
   return 0;
 }
 

@@ -61,6 +61,10 @@ struct KArgs {
   uint32_t *err;     // [R]
   // accumulators: [T][nstates] counts ++ formed[T] ++ broken[T] ++ events[4]
   unsigned long long *acc;
+  unsigned long long *acc_rep; // optional per-replica counts [R][nstates]
+  const uint8_t *skip;         // optional [R]: replica sits this launch out
+  // RNG identity of replica j of transition t: t * rng_total + rng_first + j
+  uint32_t rng_first, rng_total;
   int n_trans;
   // optional samples
   double *dist;          // [R][dist_cap][n_nonlocal_max]

@@ -65,6 +65,15 @@
 #define HMC_COLD __forceinline__
 #endif
 
+// -DHMC_PF_UNROLL=n: unroll factor of the pre-filter loop (experiment switch)
+#define HMC_STR_(x) #x
+#define HMC_PRAGMA_(x) _Pragma(HMC_STR_(x))
+#ifdef HMC_PF_UNROLL
+#define HMC_PF_UNROLL_PRAGMA HMC_PRAGMA_(unroll HMC_PF_UNROLL)
+#else
+#define HMC_PF_UNROLL_PRAGMA
+#endif
+
 namespace {
 
 // ----------------------------------------------------------------- helpers --
@@ -159,6 +168,11 @@ struct Rep {
 enum { REP_LIVE = 1u,   // not a clone filling an idle group of the warp: has global side effects
        REP_TRACING = 2u };
 __device__ __forceinline__ bool rep_live(const Rep &R) { return (R.flags & REP_LIVE) != 0u; }
+// RNG identity: replica index in the whole (possibly multi-rank) ensemble
+__device__ __forceinline__ unsigned rep_rng_id(const KArgs &a, const Rep &R) {
+  return unsigned(R.trans) * a.rng_total + a.rng_first +
+         unsigned(R.r - R.trans * a.replicas_per_trans);
+}
 __device__ __forceinline__ double *rep_sbias(const KArgs &a, const Rep &R) {
   return a.s_bias + size_t(R.r) * a.nstates;
 }
@@ -746,6 +760,7 @@ __device__ HMC_COLD StepOut init_step(const KArgs &a, const Rep &R_in, const Sme
   if (on && !(ok & 2u)) R.err |= HMC_ERR_NONLOCAL_OVERLAP;
 
   // init_cells (hardspheres.cc:334-369) + raw velocity draws (init_vel :197-209)
+  const unsigned rng_id = rep_rng_id(a, R);
   for (int k = lane; k < nb && on; k += G) {
     double x = BX(s, k), y = BY(s, k), z = BZ(s, k);
     x -= floor(x * a.inv_l) * a.l; // Box::minpos
@@ -768,9 +783,9 @@ __device__ HMC_COLD StepOut init_step(const KArgs &a, const Rep &R_in, const Sme
       // counter = (2k+c, draw_lo, draw_hi, replica)
       const uint2 key = make_uint2(a.seed0, a.seed1);
       const uint4 c0 = philox4x32(
-          make_uint4(2u * k, unsigned(draw), unsigned(draw >> 32), unsigned(R.r)), key);
+          make_uint4(2u * k, unsigned(draw), unsigned(draw >> 32), rng_id), key);
       const uint4 c1 = philox4x32(
-          make_uint4(2u * k + 1u, unsigned(draw), unsigned(draw >> 32), unsigned(R.r)), key);
+          make_uint4(2u * k + 1u, unsigned(draw), unsigned(draw >> 32), rng_id), key);
       const double r0 = sqrt(-2.0 * log(u53(c0.x, c0.y)));
       double sn, cs;
       sincospi(2.0 * u53(c0.z, c0.w), &sn, &cs);
@@ -931,8 +946,11 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
     const double t = bt;
     const bool is_cell = bk < PAIR_KEY;
     const int nbead = is_cell ? 1 : 2; // beads whose slots are re-predicted
-    const int bi = int((bk >> 16) & 0xffu);
-    const int bj = is_cell ? bi : int((bk >> 8) & 0xffu);
+    int bi = int((bk >> 16) & 0xffu);
+    int bj = is_cell ? bi : int((bk >> 8) & 0xffu);
+    // (opaque to the compiler: it would otherwise re-derive the two indices from the key at
+    // every use in the partner loops instead of keeping them in registers)
+    asm volatile("" : "+r"(bi), "+r"(bj));
     const int pidx = bi * PINFO_STRIDE + bj;
     const int dij = bj - bi;
     // the wall latched at the prediction of a crossing (t_until_cell :589-666)
@@ -1168,6 +1186,7 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
         // advance and one box for the wrap
         const unsigned long long bm0 = __ldg(&R.bmask[bi]), bm1 = __ldg(&R.bmask[bj]);
         int cnt = 0;
+        HMC_PF_UNROLL_PRAGMA
         for (int base = 0; base < nb; base += G) {
           const int kk = base + lane;
           const bool kin = kk < nb;
@@ -1370,8 +1389,10 @@ __device__ HMC_COLD unsigned sample_step(const KArgs &a, const Rep &R_in, const 
   }
   const bool rec = on && (step % a.write_step == 0);
   if (rec) {
-    if (lane == 0 && rep_live(R) && R.config < (unsigned long long)a.nstates)
+    if (lane == 0 && rep_live(R) && R.config < (unsigned long long)a.nstates) {
       atomicAdd(&a.acc[size_t(trans) * a.nstates + R.config], 1ull);
+      if (a.acc_rep) a.acc_rep[size_t(R.r) * a.nstates + R.config] += 1ull; // (its only writer)
+    }
     record_config_int(a, R, lane);
   }
   // unique_config: first recorded sample with config == 1 (main.cc:211-216)
@@ -1639,7 +1660,7 @@ __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hmc_ensemble_kernel
       ws.philox = (a.rng_mode == HMC_RNG_PHILOX);
       ws.key = make_uint2(a.seed0, a.seed1);
       ws.c1 = ws.c2 = 0;
-      ws.c3 = unsigned(r);
+      ws.c3 = rep_rng_id(a, R);
       ws.buf_blk = 0xffffffffu;
       ws.moves_done = 0;
       return ws;
@@ -1692,7 +1713,8 @@ __global__ void __launch_bounds__(HMC_BLOCK, HMC_MIN_BLOCKS) hmc_ensemble_kernel
       const unsigned per = wl ? a.nsteps_wl : (a.op == HMC_OP_RUN ? (a.phase == HMC_PHASE_EQ ? a.nsteps_eq : a.nsteps) : 1u);
       const unsigned nunits = wl && a.op == HMC_OP_RUN ? a.count * unsigned(a.nstates) : a.count;
       const unsigned E = nunits * per; // units: iterations (RUN), trajectories (WL), steps (MD_ONLY)
-      unsigned e = 0;                  // next / current event step of this group
+      // (a skipped replica's schedule is empty)
+      unsigned e = (a.skip && a.skip[r]) ? E : 0u; // next / current event step of this group
       unsigned ninit = 0;              // initialize_system calls so far (RNG draw index)
       bool in_step = false;
       double step_time = 0.0, e0 = 0.0;

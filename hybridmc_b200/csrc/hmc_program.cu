@@ -6,8 +6,11 @@
 //                             draws init_vel's normals and the crankshaft word tape with
 //                             libstdc++ exactly as the reference does and injects them,
 //                             so the GPU trajectory is the reference's, bit for bit.
-//   hmc_run_program_ensemble  R replicas with device Philox streams and pooled counts
-//                             (the production path).
+//   hmc_run_program_ensemble  T transitions x R replicas with device Philox streams and
+//                             pooled counts (the production path), optionally spread
+//                             over the ranks of an hmc_comm (one NCCL all-reduce of the
+//                             counts per G-test round), or with every replica running
+//                             its own program (independent mode).
 // Only orchestration and O(nstates) arithmetic happen here; every trajectory
 // operation runs in the CUDA kernel.
 #include "hmc_internal.h"
@@ -230,7 +233,14 @@ int hmc_run_program_exact_sink(const hmc_params *p, int device, const double *po
         done += moves_done;
       }
     }
-    RUN(hmc_get_counts(h, cc.data(), int(ns), nullptr, nullptr, nullptr));
+    uint32_t round_err = 0;
+    RUN(hmc_get_counts(h, cc.data(), int(ns), nullptr, nullptr, &round_err));
+    // the reference throws at the first violated check (main.cc:48-56,219-225): stop at the
+    // end of the round that raised a flag instead of running on to max_g_test_count
+    if (round_err & ~uint32_t(HMC_ERR_TAPE_UNDERRUN)) {
+      gcount++;
+      break;
+    }
     if (dist_cap) { // DistWriter appends one row per MD step (main.cc:199-200)
       std::vector<double> rows(size_t(dist_cap) * std::max(1u, p->n_nonlocal));
       uint32_t n = 0;
@@ -293,3 +303,360 @@ int hmc_run_program_exact_sink(const hmc_params *p, int device, const double *po
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------ ensemble program --
+
+namespace {
+
+struct EnsembleFail {
+  hmc_handle h;
+  hmc_ensemble_totals *tot;
+  int operator()(int rc, const char *what) const {
+    if (tot) std::snprintf(tot->message, sizeof tot->message, "%s: %s", what,
+                           hmc_last_error(h) && *hmc_last_error(h) ? hmc_last_error(h)
+                                                                   : hmc_last_error(nullptr));
+    if (h) hmc_destroy(h);
+    return rc;
+  }
+};
+
+#define ERUN(call)                                                                       \
+  do {                                                                                   \
+    const int rc_ = (call);                                                              \
+    if (rc_ != 0) return efail(rc_, #call);                                              \
+  } while (0)
+
+// flags that end a program (the reference throws at these points); a full sample buffer
+// only drops samples
+const uint32_t FATAL_FLAGS = ~uint32_t(HMC_ERR_SAMPLE_OVERFLOW);
+
+} // namespace
+
+extern "C" int hmc_run_program_ensemble(const hmc_params *tr, int T, int device,
+                                        const double *start_pos,
+                                        const hmc_ensemble_options *opt,
+                                        const hmc_ensemble_sink *sink, hmc_ensemble_result *res,
+                                        hmc_ensemble_totals *tot) {
+  if (tot) std::memset(tot, 0, sizeof *tot);
+  if (!tr || T < 1 || !start_pos || !opt || !res || opt->replicas < 1) {
+    if (tot) std::snprintf(tot->message, sizeof tot->message, "hmc_run_program_ensemble: bad arguments");
+    return -1;
+  }
+  const hmc_ensemble_sink no_sink{};
+  if (!sink) sink = &no_sink;
+  const hmc_params &p = tr[0];
+  const unsigned nb = p.nbeads, ns = 1u << p.n_transient, R = opt->replicas;
+  if (ns > 16) {
+    if (tot) std::snprintf(tot->message, sizeof tot->message, "more than 16 states");
+    return -1;
+  }
+  hmc_comm comm = opt->independent ? nullptr : opt->comm;
+  const unsigned world = unsigned(hmc_comm_world(comm)), rank = unsigned(hmc_comm_rank(comm));
+  const size_t Rl = size_t(T) * R; // replicas of this rank
+  for (int t = 0; t < T; t++) std::memset(&res[t], 0, sizeof res[t]);
+
+  hmc_handle h = nullptr;
+  {
+    const int rc = hmc_create(tr, T, int(R), device, &h);
+    if (rc != 0) {
+      if (tot) std::snprintf(tot->message, sizeof tot->message, "%s", hmc_last_error(nullptr));
+      return rc;
+    }
+  }
+  const EnsembleFail efail{h, tot};
+  ERUN(hmc_set_replica_ids(h, rank * R, R * world));
+  {
+    std::vector<double> pos(Rl * nb * 3);
+    for (int t = 0; t < T; t++)
+      for (unsigned j = 0; j < R; j++)
+        std::memcpy(&pos[(size_t(t) * R + j) * nb * 3], start_pos + size_t(t) * nb * 3,
+                    sizeof(double) * nb * 3);
+    ERUN(hmc_set_positions(h, pos.data()));
+  }
+  ERUN(hmc_seed(h, opt->seed0, opt->seed1));
+  ERUN(hmc_init_config_from_positions(h));
+  std::vector<double> sb(size_t(T) * ns); // pooled mode: one row per transition
+  for (int t = 0; t < T; t++)
+    for (unsigned i = 0; i < ns; i++) // init_s, entropy.cc:14-20
+      sb[size_t(t) * ns + i] = 3 * (p.n_transient - unsigned(__builtin_popcount(i)));
+  ERUN(hmc_set_s_bias(h, sb.data(), int(ns)));
+  if (opt->hist_bins) ERUN(hmc_enable_dist_hist(h, opt->hist_bins, opt->hist_rmax));
+  if (opt->independent) ERUN(hmc_enable_replica_counts(h, 1));
+
+  const unsigned iters = opt->iters_per_round
+                             ? opt->iters_per_round
+                             : std::max(1u, (p.total_iter + R * world - 1) / (R * world));
+  const unsigned eq = opt->eq_iters ? opt->eq_iters : std::max(1u, std::min(p.total_iter_eq, 8u));
+  const unsigned cap = opt->max_rounds ? opt->max_rounds : p.max_g_test_count;
+  const unsigned rows_round = iters * p.nsteps; // dist rows a replica produces per round
+  const unsigned dist_cap =
+      (opt->dist_rows && sink->on_dist) ? std::min(rows_round, (opt->dist_rows + R - 1) / R) : 0;
+  const unsigned cfg_round = iters * p.nsteps / p.write_step + 2 + iters * p.mc_write;
+  const unsigned cfg_cap = (opt->config_int_rows && sink->on_config_int)
+                               ? std::min(cfg_round, (opt->config_int_rows + R - 1) / R)
+                               : 0;
+  if (dist_cap || cfg_cap) ERUN(hmc_enable_samples(h, dist_cap, cfg_cap));
+  unsigned nl_max = 1;
+  for (int t = 0; t < T; t++) nl_max = std::max(nl_max, tr[t].n_nonlocal);
+
+  const auto t0 = std::chrono::steady_clock::now();
+  double dev_ms = 0.0;
+  auto add_ms = [&]() {
+    uint64_t n = 0;
+    float ms = 0.f;
+    if (hmc_get_launch_stats(h, &n, &ms) == 0) dev_ms += ms;
+  };
+
+  // equilibration, main.cc:411-431
+  ERUN(hmc_reset_clocks(h));
+  ERUN(hmc_run(h, HMC_PHASE_EQ, 0, eq));
+  ERUN(hmc_sync(h));
+  add_ms();
+  ERUN(hmc_init_config_from_positions(h));
+  ERUN(hmc_reset_clocks(h));
+
+  // Wang-Landau, main.cc:433-441: every replica its own estimate
+  std::vector<double> sb_rep(Rl * ns);
+  if (opt->wang_landau) {
+    const unsigned nwl = wl_iters(p);
+    if (nwl) {
+      ERUN(hmc_run(h, HMC_PHASE_WL, 0, nwl));
+      ERUN(hmc_sync(h));
+      add_ms();
+    }
+    ERUN(hmc_get_s_bias(h, sb_rep.data(), int(ns)));
+    if (!opt->independent) {
+      // pooled start value: the mean over all replicas of the transition, formed from
+      // exact fixed-point sums (2^-32 resolution) so that it does not depend on how the
+      // replicas are spread over ranks
+      std::vector<uint64_t> fx(size_t(T) * ns, 0);
+      for (size_t r = 0; r < Rl; r++)
+        for (unsigned i = 0; i < ns; i++)
+          fx[(r / R) * ns + i] += uint64_t(int64_t(std::llround(sb_rep[r * ns + i] * 4294967296.0)));
+      ERUN(hmc_comm_allreduce_host_u64(comm, fx.data(), fx.size(), 0));
+      for (size_t k = 0; k < fx.size(); k++)
+        sb[k] = double(int64_t(fx[k])) / (4294967296.0 * double(R) * double(world));
+      ERUN(hmc_set_s_bias(h, sb.data(), int(ns)));
+    }
+  } else if (opt->independent) {
+    ERUN(hmc_get_s_bias(h, sb_rep.data(), int(ns)));
+  }
+
+  // the G-test rounds, main.cc:451-491
+  std::vector<uint8_t> done_t(T, 0), skip(Rl, 0), done_r(opt->independent ? Rl : 0, 0);
+  std::vector<uint32_t> rounds_r(opt->independent ? Rl : 0, 0);
+  std::vector<uint64_t> cc(size_t(T) * ns), cc_rep(opt->independent ? Rl * ns : 0);
+  std::vector<uint32_t> err(Rl);
+  std::vector<uint64_t> err_t(T);
+  std::vector<double> dist_buf;
+  std::vector<uint32_t> dist_n;
+  std::vector<uint64_t> cfg_buf;
+  std::vector<uint32_t> cfg_n;
+  int rc_final = 0;
+  for (unsigned rnd = 0; rnd < cap; rnd++) {
+    ERUN(hmc_reset_clocks(h));
+    ERUN(hmc_reset_counts(h));
+    ERUN(hmc_set_replica_skip(h, skip.data()));
+    ERUN(hmc_run(h, HMC_PHASE_MAIN, 0, iters));
+    ERUN(hmc_allreduce_counts(h, comm)); // the round's one exchange (on the engine's stream)
+    ERUN(hmc_get_counts(h, cc.data(), int(ns), nullptr, nullptr, err.data()));
+    add_ms();
+    // replica error flags end the program, as the reference's exceptions do
+    for (int t = 0; t < T; t++) {
+      uint32_t e = 0;
+      for (unsigned j = 0; j < R; j++) e |= err[size_t(t) * R + j];
+      err_t[t] = e;
+    }
+    if (comm && world > 1) {
+      // OR over ranks, bit by bit (the sum of 0/1 flags per bit is exact)
+      std::vector<uint64_t> bits(size_t(T) * 32);
+      for (int t = 0; t < T; t++)
+        for (int b = 0; b < 32; b++) bits[size_t(t) * 32 + b] = (err_t[t] >> b) & 1u;
+      ERUN(hmc_comm_allreduce_host_u64(comm, bits.data(), bits.size(), 1));
+      for (int t = 0; t < T; t++) {
+        uint64_t e = 0;
+        for (int b = 0; b < 32; b++) e |= (bits[size_t(t) * 32 + b] ? 1ull : 0ull) << b;
+        err_t[t] = e;
+      }
+    }
+    bool fatal = false;
+    for (int t = 0; t < T; t++) {
+      res[t].err_flags |= uint32_t(err_t[t]);
+      if (uint32_t(err_t[t]) & FATAL_FLAGS) fatal = true;
+    }
+    if (dist_cap) {
+      dist_buf.resize(Rl * dist_cap * nl_max);
+      dist_n.resize(Rl);
+      ERUN(hmc_get_dist(h, dist_buf.data(), dist_n.data()));
+      std::vector<double> rows;
+      for (int t = 0; t < T; t++) {
+        if (done_t[t]) continue;
+        rows.clear();
+        const unsigned nbonds = tr[t].n_nonlocal;
+        for (unsigned j = 0; j < R; j++) {
+          const size_t r = size_t(t) * R + j;
+          const unsigned n = std::min(dist_n[r], dist_cap);
+          for (unsigned q = 0; q < n; q++) {
+            const double *src = &dist_buf[(r * dist_cap + q) * nl_max];
+            rows.insert(rows.end(), src, src + nbonds);
+          }
+        }
+        if (nbonds) sink->on_dist(sink->user, t, rows.data(), unsigned(rows.size() / nbonds), nbonds);
+      }
+    }
+    if (cfg_cap) {
+      cfg_buf.resize(Rl * cfg_cap);
+      cfg_n.resize(Rl);
+      ERUN(hmc_get_config_int(h, cfg_buf.data(), cfg_n.data()));
+      std::vector<uint64_t> vals;
+      for (int t = 0; t < T; t++) {
+        if (done_t[t]) continue;
+        vals.clear();
+        for (unsigned j = 0; j < R; j++) {
+          const size_t r = size_t(t) * R + j;
+          const unsigned n = std::min(cfg_n[r], cfg_cap);
+          vals.insert(vals.end(), &cfg_buf[r * cfg_cap], &cfg_buf[r * cfg_cap] + n);
+        }
+        sink->on_config_int(sink->user, t, vals.data(), unsigned(vals.size()));
+      }
+    }
+    if (fatal) {
+      rc_final = -8;
+      if (tot) std::snprintf(tot->message, sizeof tot->message,
+                             "replica error flags raised in round %u (see err_flags)", rnd);
+      break;
+    }
+    bool all_done = true;
+    if (!opt->independent) {
+      for (int t = 0; t < T; t++) {
+        if (done_t[t]) continue;
+        uint64_t *c = &cc[size_t(t) * ns];
+        double *s = &sb[size_t(t) * ns];
+        hmc_compute_entropy(c, s, int(ns), p.pos_scale, p.neg_scale);
+        double gv = 0, gc = 0, pv = 0;
+        const int ok = hmc_g_test(c, int(ns), p.sig_level, &gv, &gc, &pv);
+        res[t].rounds++;
+        res[t].accepted = ok;
+        for (unsigned i = 0; i < ns; i++) {
+          res[t].s_bias[i] = s[i];
+          res[t].config_count[i] = c[i];
+        }
+        if (sink->on_round) sink->on_round(sink->user, t, rnd, c, s, int(ns), ok, gv, gc, pv);
+        if (ok) {
+          done_t[t] = 1;
+          for (unsigned j = 0; j < R; j++) skip[size_t(t) * R + j] = 1;
+        } else {
+          all_done = false;
+        }
+      }
+      ERUN(hmc_set_s_bias(h, sb.data(), int(ns)));
+    } else {
+      ERUN(hmc_get_replica_counts(h, cc_rep.data()));
+      for (size_t r = 0; r < Rl; r++) {
+        if (done_r[r]) continue;
+        uint64_t *c = &cc_rep[r * ns];
+        double *s = &sb_rep[r * ns];
+        hmc_compute_entropy(c, s, int(ns), p.pos_scale, p.neg_scale);
+        rounds_r[r]++;
+        if (hmc_g_test(c, int(ns), p.sig_level, nullptr, nullptr, nullptr)) {
+          done_r[r] = 1;
+          skip[r] = 1;
+        } else {
+          all_done = false;
+        }
+      }
+      ERUN(hmc_set_s_bias_per_replica(h, sb_rep.data(), int(ns)));
+      for (int t = 0; t < T; t++) {
+        res[t].rounds = rnd + 1;
+        bool every = true;
+        for (unsigned j = 0; j < R; j++) every = every && done_r[size_t(t) * R + j];
+        res[t].accepted = every ? 1 : 0;
+        for (unsigned i = 0; i < ns; i++) res[t].config_count[i] = cc[size_t(t) * ns + i];
+      }
+    }
+    if (all_done) break;
+  }
+
+  // totals, histograms, hand-off structures
+  ERUN(hmc_allreduce_totals(h, comm));
+  {
+    std::vector<uint64_t> formed(T), broken(T);
+    ERUN(hmc_get_counts(h, nullptr, int(ns), formed.data(), broken.data(), nullptr));
+    for (int t = 0; t < T; t++) {
+      res[t].formed = formed[t];
+      res[t].broken = broken[t];
+    }
+    uint64_t ev[4];
+    ERUN(hmc_get_event_counts(h, ev));
+    if (tot) {
+      tot->collisions = ev[0];
+      tot->cell_crossings = ev[1];
+    }
+  }
+  if (opt->hist_bins) {
+    ERUN(hmc_allreduce_hist(h, comm));
+    if (sink->on_hist) {
+      std::vector<uint64_t> hist(size_t(T) * nl_max * 2 * opt->hist_bins);
+      ERUN(hmc_get_dist_hist(h, hist.data()));
+      for (int t = 0; t < T; t++)
+        sink->on_hist(sink->user, t, &hist[size_t(t) * nl_max * 2 * opt->hist_bins], nl_max,
+                      opt->hist_bins);
+    }
+  }
+  {
+    // unique_config (main.cc:211-216): the bonded structure of the lowest replica id that
+    // recorded one; only its owner contributes non-zero words to the (exact) sum
+    std::vector<double> up(Rl * nb * 3), uv(Rl * nb * 3);
+    std::vector<uint8_t> found(Rl);
+    ERUN(hmc_get_unique_config(h, up.data(), uv.data(), found.data()));
+    std::vector<uint64_t> key(T);
+    std::vector<int> local(T, -1);
+    for (int t = 0; t < T; t++) {
+      key[t] = ~0ull;
+      for (unsigned j = 0; j < R; j++)
+        if (found[size_t(t) * R + j]) {
+          local[t] = int(j);
+          key[t] = uint64_t(rank) * R + j;
+          break;
+        }
+    }
+    std::vector<uint64_t> best = key;
+    ERUN(hmc_comm_allreduce_host_u64(comm, best.data(), best.size(), 2));
+    const size_t words = size_t(nb) * 3;
+    std::vector<uint64_t> pack(size_t(T) * words * 2, 0);
+    for (int t = 0; t < T; t++)
+      if (local[t] >= 0 && key[t] == best[t]) {
+        const size_t r = size_t(t) * R + size_t(local[t]);
+        std::memcpy(&pack[size_t(t) * words * 2], &up[r * words], sizeof(double) * words);
+        std::memcpy(&pack[size_t(t) * words * 2 + words], &uv[r * words], sizeof(double) * words);
+      }
+    ERUN(hmc_comm_allreduce_host_u64(comm, pack.data(), pack.size(), 0));
+    for (int t = 0; t < T; t++) {
+      res[t].have_unique = best[t] != ~0ull;
+      if (res[t].have_unique) {
+        std::memcpy(res[t].unique_pos, &pack[size_t(t) * words * 2], sizeof(double) * words);
+        std::memcpy(res[t].unique_vel, &pack[size_t(t) * words * 2 + words], sizeof(double) * words);
+      }
+    }
+  }
+  if (opt->independent) {
+    for (int t = 0; t < T; t++) {
+      if (sink->on_replicas)
+        sink->on_replicas(sink->user, t, &sb_rep[size_t(t) * R * ns], &rounds_r[size_t(t) * R],
+                          &done_r[size_t(t) * R], R, int(ns));
+      // the transition's value: mean over its replicas (tools/avg_s_bias.py averages seeds)
+      for (unsigned i = 0; i < ns; i++) {
+        double m = 0.0;
+        for (unsigned j = 0; j < R; j++) m += sb_rep[(size_t(t) * R + j) * ns + i];
+        res[t].s_bias[i] = m / double(R);
+      }
+    }
+  }
+  if (tot) {
+    tot->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    tot->seconds_device = dev_ms * 1e-3;
+    tot->collectives = hmc_comm_collectives(comm);
+  }
+  hmc_destroy(h);
+  return rc_final;
+}

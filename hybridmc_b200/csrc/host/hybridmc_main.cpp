@@ -19,6 +19,7 @@
 #include "mini_json.h"
 
 #include <cerrno>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -283,6 +284,22 @@ void on_snapshot(void *u, const double *pos, const double *sb, int ns, uint64_t 
     throw std::runtime_error(std::string("snapshot: ") + std::strerror(errno));
 }
 
+// ---- ensemble mode (--replicas R): hooks of hmc_run_program_ensemble ----------------
+void ens_on_round(void *u, int, unsigned rnd, const uint64_t *cc, const double *sb, int ns,
+                  int accepted, double g, double crit, double pv) {
+  on_round(u, rnd, cc, sb, ns, accepted, g, crit, pv);
+}
+void ens_on_dist(void *u, int, const double *rows, unsigned n, unsigned nbonds) {
+  on_dist(u, rows, n, nbonds);
+}
+void ens_on_config_int(void *u, int, const uint64_t *c, unsigned n) { on_config_int(u, c, n); }
+void ens_on_hist(void *u, int, const uint64_t *hist, unsigned n_nonlocal, unsigned nbins) {
+  // pooled distance histograms, split by the state of the transient bond: the sufficient
+  // statistics of tools/mfpt.py (hybridmc_b200/mfpt.py reads them)
+  static_cast<Output *>(u)->file.put(0, "dist_hist", U64, {n_nonlocal, 2, nbins}, hist,
+                                     sizeof(uint64_t) * size_t(n_nonlocal) * 2 * nbins);
+}
+
 void write_bond_attr(Container &f, const char *name, const uint32_t (*b)[2], uint32_t n) {
   f.put(1, name, U32, {n, 2}, b, sizeof(uint32_t) * 2 * n); // NonlocalBonds::write_hdf5
 }
@@ -296,7 +313,19 @@ void usage() {
                "  --input-file arg      input: unique_config/pos of a previous layer\n"
                "  --snapshot-file arg   snapshot\n"
                "  --device arg (=0)     CUDA device\n"
-               "  --output-format arg (=hdf5)  hdf5 | hmcb\n";
+               "  --output-format arg (=hdf5)  hdf5 | hmcb\n"
+               "ensemble mode (the production path; without --replicas: one replica fed the\n"
+               "reference's std::mt19937 stream, bit-identical to the reference):\n"
+               "  --replicas arg        replicas of the transition on this GPU, pooled counts\n"
+               "  --iters-per-round arg iterations per replica and G-test round\n"
+               "                        (default total_iter / replicas, rounded up)\n"
+               "  --eq-iters arg        equilibration iterations (default min(total_iter_eq, 8))\n"
+               "  --max-rounds arg      G-test rounds at most (default max_g_test_count)\n"
+               "  --no-wl               skip the Wang-Landau pre-estimate\n"
+               "  --hist-bins arg (=0)  pooled distance histograms -> dataset dist_hist\n"
+               "  --nccl-id-file arg    multi-GPU: one process per GPU (RANK, WORLD_SIZE,\n"
+               "                        LOCAL_RANK in the environment), the replicas of the\n"
+               "                        transition are split over the ranks; rank 0 writes\n";
 }
 
 } // namespace
@@ -310,6 +339,9 @@ int main(int argc, char *argv[]) {
   std::string input_name, snapshot_name;
   int device = 0;
   bool hdf5 = true;
+  unsigned replicas = 0, iters_per_round = 0, eq_iters = 0, max_rounds = 0, hist_bins = 0;
+  bool no_wl = false, device_given = false;
+  std::string nccl_id_file;
   try {
     for (int i = 1; i < argc; i++) {
       std::string a = argv[i], val;
@@ -334,7 +366,16 @@ int main(int argc, char *argv[]) {
       else if (take("snapshot-file")) snapshot_name = val;
       else if (take("json-file")) positional.insert(positional.begin(), val);
       else if (take("output-file")) positional.push_back(val);
-      else if (take("device")) device = std::atoi(val.c_str());
+      else if (take("device")) {
+        device = std::atoi(val.c_str());
+        device_given = true;
+      } else if (take("replicas")) replicas = unsigned(std::atoi(val.c_str()));
+      else if (take("iters-per-round")) iters_per_round = unsigned(std::atoi(val.c_str()));
+      else if (take("eq-iters")) eq_iters = unsigned(std::atoi(val.c_str()));
+      else if (take("max-rounds")) max_rounds = unsigned(std::atoi(val.c_str()));
+      else if (take("hist-bins")) hist_bins = unsigned(std::atoi(val.c_str()));
+      else if (take("nccl-id-file")) nccl_id_file = val;
+      else if (a == "--no-wl") no_wl = true;
       else if (take("output-format")) {
         if (val != "hdf5" && val != "hmcb")
           throw std::runtime_error("the argument ('" + val + "') for option '--output-format' is invalid");
@@ -410,6 +451,66 @@ int main(int argc, char *argv[]) {
       pos_in.resize(3 * p.nbeads);
       std::memcpy(pos_in.data(), rp->bytes.data(), sizeof(double) * 3 * p.nbeads);
       pos_ptr = pos_in.data();
+    }
+
+    if (replicas > 0) {
+      // ---- ensemble mode: hmc_run_program_ensemble for this one transition ----
+      int rank = 0, world = 1;
+      hmc_comm comm = nullptr;
+      if (!nccl_id_file.empty()) {
+        if (const char *e = std::getenv("RANK")) rank = std::atoi(e);
+        if (const char *e = std::getenv("WORLD_SIZE")) world = std::atoi(e);
+        if (!device_given)
+          if (const char *e = std::getenv("LOCAL_RANK")) device = std::atoi(e);
+        if (world > 1 && hmc_comm_create_from_file(nccl_id_file.c_str(), rank, world, device, &comm) != 0)
+          throw std::runtime_error(std::string("NCCL: ") + hmc_last_error(nullptr));
+      }
+      std::vector<double> start(3 * p.nbeads);
+      if (pos_ptr) std::memcpy(start.data(), pos_ptr, sizeof(double) * start.size());
+      else if (snap_ptr) std::memcpy(start.data(), snap.pos, sizeof(double) * start.size());
+      else if (hmc_init_pos_chain(&p, p.seeds, p.n_seeds, start.data()) != 0)
+        throw std::runtime_error("number of tries exceeded while placing bead in box");
+      hmc_ensemble_options opt{};
+      opt.replicas = replicas;
+      opt.iters_per_round = iters_per_round;
+      opt.eq_iters = eq_iters;
+      opt.max_rounds = max_rounds;
+      opt.wang_landau = no_wl ? 0u : 1u;
+      opt.hist_bins = hist_bins;
+      opt.hist_rmax = p.length * 0.5 * std::sqrt(3.0); // the longest min-image distance
+      opt.dist_rows = p.total_iter * p.nsteps;          // the reference's rows per round
+      opt.config_int_rows = p.total_iter * p.nsteps / p.write_step + p.total_iter * p.mc_write;
+      opt.seed0 = p.n_seeds > 0 ? p.seeds[0] : 1u;
+      opt.seed1 = p.n_seeds > 1 ? p.seeds[1] : 0u;
+      opt.comm = comm;
+      hmc_ensemble_sink es{};
+      es.user = &out;
+      if (rank == 0) {
+        es.on_round = ens_on_round;
+        es.on_hist = ens_on_hist;
+      }
+      es.on_dist = ens_on_dist; // (each rank keeps its own rows; rank 0's go to the file)
+      es.on_config_int = ens_on_config_int;
+      hmc_ensemble_result er;
+      hmc_ensemble_totals tot;
+      const int rc = hmc_run_program_ensemble(&p, 1, device, start.data(), &opt, &es, &er, &tot);
+      if (comm) hmc_comm_destroy(comm);
+      if (er.err_flags & HMC_ERR_LOCAL_OVERLAP) throw std::runtime_error("local beads overlap");
+      if (er.err_flags & HMC_ERR_NONLOCAL_OVERLAP) throw std::runtime_error("nonlocal beads overlap");
+      if (er.err_flags & HMC_ERR_ENERGY) throw std::runtime_error("energy is not conserved");
+      if (rc != 0) throw std::runtime_error(tot.message);
+      if (rank == 0) {
+        if (er.have_unique) on_unique(&out, er.unique_pos, er.unique_vel, 1, p.nbeads);
+        if (hist_bins) out.file.put(1, "dist_hist_rmax", F64, {}, &opt.hist_rmax, sizeof(double));
+        const std::string tmp = output_name + ".tmp";
+        if (!out.file.write(tmp, false) || std::rename(tmp.c_str(), output_name.c_str()) != 0)
+          throw std::runtime_error("cannot write " + output_name + ": " + std::strerror(errno));
+        std::cerr << "hybridmc-b200: ensemble of " << replicas << " x " << world << " replicas, "
+                  << tot.collisions << " collision events, " << er.rounds << " G-test rounds"
+                  << (er.accepted ? " (accepted), " : " (not accepted), ") << tot.seconds << " s ("
+                  << tot.seconds_device << " s on the device)" << std::endl;
+      }
+      return 0;
     }
 
     hmc_sink sink{};

@@ -39,6 +39,12 @@ EXPORTS = [
     "hmc_run_program_exact_sink", "hmc_get_schedule_state", "hmc_set_schedule_state",
     "hmc_set_s_bias_per_replica",
     "hmc_dist_hist_device_ptr",
+    "hmc_comm_unique_id", "hmc_comm_create", "hmc_comm_create_from_file", "hmc_comm_destroy",
+    "hmc_comm_rank", "hmc_comm_world", "hmc_comm_nccl_version", "hmc_comm_collectives",
+    "hmc_allreduce_counts", "hmc_allreduce_totals", "hmc_allreduce_hist",
+    "hmc_comm_allreduce_host_u64", "hmc_comm_bcast_host", "hmc_comm_allreduce_device_u64",
+    "hmc_set_replica_ids", "hmc_enable_replica_counts", "hmc_get_replica_counts",
+    "hmc_set_replica_skip", "hmc_run_program_ensemble",
     "hmc_h5_create", "hmc_h5_dataset", "hmc_h5_attribute", "hmc_h5_write", "hmc_h5_destroy",
 ]
 
@@ -77,6 +83,22 @@ def load_library(path=None):
     lib.hmc_g_test.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                C.c_void_p]
     lib.hmc_enable_dist_hist.argtypes = [C.c_void_p, C.c_uint, C.c_double]
+    lib.hmc_comm_collectives.restype = C.c_uint64
+    lib.hmc_comm_collectives.argtypes = [C.c_void_p]
+    lib.hmc_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.hmc_comm_create_from_file.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                              C.POINTER(C.c_void_p)]
+    for name in ("hmc_comm_destroy", "hmc_comm_rank", "hmc_comm_world"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.hmc_allreduce_counts.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hmc_allreduce_totals.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hmc_allreduce_hist.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hmc_comm_allreduce_host_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    lib.hmc_comm_bcast_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    lib.hmc_set_replica_ids.argtypes = [C.c_void_p, C.c_uint, C.c_uint]
+    lib.hmc_enable_replica_counts.argtypes = [C.c_void_p, C.c_int]
+    lib.hmc_get_replica_counts.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hmc_set_replica_skip.argtypes = [C.c_void_p, C.c_void_p]
     for name in ("hmc_destroy", "hmc_set_positions", "hmc_get_positions", "hmc_get_velocities",
                  "hmc_set_config", "hmc_get_config", "hmc_init_config_from_positions",
                  "hmc_reset_clocks", "hmc_reset_counts", "hmc_sync", "hmc_get_event_counts",
@@ -116,6 +138,37 @@ class Engine:
         self._dist_cap = 0
         self._cfg_cap = 0
         self._hist_bins = 0
+
+    # -- multi-GPU / independent-program mode --
+    def set_replica_ids(self, first, total_per_transition):
+        """RNG identity of this handle's replicas inside a multi-rank ensemble."""
+        self._ck(self.lib.hmc_set_replica_ids(self.h, int(first), int(total_per_transition)))
+
+    def allreduce_counts(self, comm):
+        """config_count summed over the ranks of `comm`, in place, on the engine's stream."""
+        self._ck(self.lib.hmc_allreduce_counts(self.h, comm.c if comm is not None else None))
+
+    def allreduce_totals(self, comm):
+        self._ck(self.lib.hmc_allreduce_totals(self.h, comm.c if comm is not None else None))
+
+    def allreduce_hist(self, comm):
+        self._ck(self.lib.hmc_allreduce_hist(self.h, comm.c if comm is not None else None))
+
+    def enable_replica_counts(self, on=True):
+        self._ck(self.lib.hmc_enable_replica_counts(self.h, 1 if on else 0))
+
+    def get_replica_counts(self):
+        out = np.zeros((self.R, self.nstates), dtype=np.uint64)
+        self._ck(self.lib.hmc_get_replica_counts(self.h, _p(out)))
+        return out
+
+    def set_replica_skip(self, skip):
+        if skip is None:
+            self._ck(self.lib.hmc_set_replica_skip(self.h, None))
+        else:
+            s = np.ascontiguousarray(skip, dtype=np.uint8)
+            assert s.shape == (self.R,)
+            self._ck(self.lib.hmc_set_replica_skip(self.h, _p(s)))
 
     # -- plumbing --
     def _ck(self, rc):
@@ -393,3 +446,211 @@ def run_program_exact(params, device=0, pos_in=None, max_gtest_iters=0, dist_row
     if rc != 0:
         raise EngineError(res.message.decode() or "hmc_run_program_exact failed (%d)" % rc)
     return res, (dist[:nrows.value] if dist is not None else None)
+
+
+# ---- multi-GPU communicator (the library's own NCCL, include/hybridmc_b200.h) ----------
+
+COMM_ID_BYTES = 128
+
+
+class Comm:
+    """hmc_comm: one rank of the all-reduce group.  `Comm.from_torch()` hands the id
+    around with torch.distributed (any backend); `Comm.from_file()` uses a shared file."""
+
+    def __init__(self, c, rank, world):
+        self.lib, self.c, self.rank, self.world = load_library(), c, rank, world
+
+    @staticmethod
+    def unique_id():
+        lib = load_library()
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        if lib.hmc_comm_unique_id(buf) != 0:
+            raise EngineError(lib.hmc_last_error(None).decode())
+        return bytes(buf)
+
+    @classmethod
+    def create(cls, id_bytes, rank, world, device):
+        lib = load_library()
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(id_bytes)
+        c = C.c_void_p()
+        if lib.hmc_comm_create(buf, int(rank), int(world), int(device), C.byref(c)) != 0:
+            raise EngineError(lib.hmc_last_error(None).decode())
+        return cls(c, rank, world)
+
+    @classmethod
+    def from_file(cls, path, rank, world, device):
+        lib = load_library()
+        c = C.c_void_p()
+        if lib.hmc_comm_create_from_file(path.encode(), int(rank), int(world), int(device),
+                                         C.byref(c)) != 0:
+            raise EngineError(lib.hmc_last_error(None).decode())
+        return cls(c, rank, world)
+
+    @classmethod
+    def from_torch(cls, device):
+        """Inside an initialised torch.distributed job (torchrun): rank 0 makes the id, the
+        default group broadcasts its 128 bytes."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls.create(box[0], rank, world, device)
+
+    def allreduce_u64(self, arr, op="sum"):
+        a = np.ascontiguousarray(arr, dtype=np.uint64)
+        rc = self.lib.hmc_comm_allreduce_host_u64(self.c, _p(a), a.size, {"sum": 0, "max": 1, "min": 2}[op])
+        if rc != 0:
+            raise EngineError(self.lib.hmc_last_error(None).decode())
+        return a
+
+    def bcast(self, arr, root=0):
+        a = np.ascontiguousarray(arr)
+        if self.lib.hmc_comm_bcast_host(self.c, _p(a), a.nbytes, int(root)) != 0:
+            raise EngineError(self.lib.hmc_last_error(None).decode())
+        return a
+
+    @property
+    def collectives(self):
+        return int(self.lib.hmc_comm_collectives(self.c))
+
+    def close(self):
+        if self.c:
+            self.lib.hmc_comm_destroy(self.c)
+            self.c = None
+
+
+# ---- the ensemble program (production path, hmc_run_program_ensemble) -------------------
+
+class EnsembleOptions(C.Structure):
+    _fields_ = [("replicas", C.c_uint32), ("iters_per_round", C.c_uint32),
+                ("eq_iters", C.c_uint32), ("max_rounds", C.c_uint32),
+                ("wang_landau", C.c_uint32), ("independent", C.c_uint32),
+                ("hist_bins", C.c_uint32), ("dist_rows", C.c_uint32),
+                ("config_int_rows", C.c_uint32), ("seed0", C.c_uint32), ("seed1", C.c_uint32),
+                ("pad", C.c_uint32), ("hist_rmax", C.c_double), ("comm", C.c_void_p)]
+
+
+class EnsembleResult(C.Structure):
+    _fields_ = [("s_bias", C.c_double * 16), ("config_count", C.c_uint64 * 16),
+                ("formed", C.c_uint64), ("broken", C.c_uint64), ("rounds", C.c_uint32),
+                ("accepted", C.c_int), ("err_flags", C.c_uint32), ("have_unique", C.c_int),
+                ("unique_pos", C.c_double * (64 * 3)), ("unique_vel", C.c_double * (64 * 3))]
+
+
+class EnsembleTotals(C.Structure):
+    _fields_ = [("collisions", C.c_uint64), ("cell_crossings", C.c_uint64),
+                ("seconds", C.c_double), ("seconds_device", C.c_double),
+                ("collectives", C.c_uint64), ("message", C.c_char * 256)]
+
+
+_ON_ROUND = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_uint, C.POINTER(C.c_uint64),
+                        C.POINTER(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double)
+_ON_DIST = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_uint, C.c_uint)
+_ON_CFG = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_uint)
+_ON_HIST = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_uint, C.c_uint)
+_ON_REPL = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint32),
+                       C.POINTER(C.c_uint8), C.c_uint, C.c_int)
+
+
+class EnsembleSink(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("on_round", _ON_ROUND), ("on_dist", _ON_DIST),
+                ("on_config_int", _ON_CFG), ("on_hist", _ON_HIST), ("on_replicas", _ON_REPL)]
+
+
+class EnsembleError(EngineError):
+    """hmc_run_program_ensemble failed; `.results` holds what it produced (err_flags)."""
+
+    def __init__(self, msg, results=None, code=0):
+        super().__init__(msg)
+        self.results, self.code = results, code
+
+
+def run_program_ensemble(params_list, start_pos, replicas, device=0, seed=(1, 2),
+                         iters_per_round=0, eq_iters=0, max_rounds=0, wl=True,
+                         independent=False, hist_bins=0, hist_rmax=0.0, dist_rows=0,
+                         config_int_rows=0, comm=None, verbose=False):
+    """hmc_run_program_ensemble: the reference's per-transition program (main.cc:411-491)
+    for T transitions of one layer x `replicas` replicas each on THIS rank, pooled over the
+    ranks of `comm`.  Returns a dict: s_bias[T][nstates], rounds[T], accepted[T], counts[T],
+    counts_rounds (per transition: the config_count row of every round), err[T], formed,
+    broken, unique_pos/unique_vel (list, None where no bonded structure was recorded),
+    dist / config_int (lists of arrays, when requested), dist_hist[T][n_nonlocal][2][bins],
+    replicas (independent mode: per transition (s_bias[R][ns], rounds[R], accepted[R])),
+    events (collisions, cell crossings), seconds, seconds_device, collectives."""
+    lib = load_library()
+    T = len(params_list)
+    p = params_list[0]
+    ns, nb = p.nstates, p.nbeads
+    arr = (HmcParams * T)(*params_list)
+    pos = np.ascontiguousarray(np.stack([np.asarray(sp, dtype=np.float64) for sp in start_pos]))
+    assert pos.shape == (T, nb, 3)
+    opt = EnsembleOptions(replicas=int(replicas), iters_per_round=int(iters_per_round),
+                          eq_iters=int(eq_iters), max_rounds=int(max_rounds),
+                          wang_landau=1 if wl else 0, independent=1 if independent else 0,
+                          hist_bins=int(hist_bins), dist_rows=int(dist_rows),
+                          config_int_rows=int(config_int_rows), seed0=int(seed[0]) & 0xffffffff,
+                          seed1=int(seed[1]) & 0xffffffff, hist_rmax=float(hist_rmax),
+                          comm=comm.c if comm is not None else None)
+    rounds_log = [[] for _ in range(T)]
+    dist = [[] for _ in range(T)]
+    cfg = [[] for _ in range(T)]
+    hist = [None] * T
+    repl = [None] * T
+
+    def on_round(_u, t, rnd, cc, sb, n, ok, g, crit, pv):
+        rounds_log[t].append(np.array([cc[i] for i in range(n)], dtype=np.uint64))
+        if verbose:
+            print("round", rnd, "transition", t, "s_bias", [sb[i] for i in range(n)], "counts",
+                  [cc[i] for i in range(n)], "ACCEPTED" if ok else "REJECTED", g, crit)
+
+    def on_dist(_u, t, rows, n, nbonds):
+        dist[t].append(np.ctypeslib.as_array(rows, shape=(n, nbonds)).copy())
+
+    def on_cfg(_u, t, vals, n):
+        cfg[t].append(np.ctypeslib.as_array(vals, shape=(n,)).copy())
+
+    def on_hist(_u, t, h, nl, nbins):
+        hist[t] = np.ctypeslib.as_array(h, shape=(nl, 2, nbins)).copy()
+
+    def on_repl(_u, t, sb, rnds, acc, R, n):
+        repl[t] = (np.ctypeslib.as_array(sb, shape=(R, n)).copy(),
+                   np.ctypeslib.as_array(rnds, shape=(R,)).copy(),
+                   np.ctypeslib.as_array(acc, shape=(R,)).astype(bool))
+
+    sink = EnsembleSink(None, _ON_ROUND(on_round),
+                        _ON_DIST(on_dist) if dist_rows else _ON_DIST(),
+                        _ON_CFG(on_cfg) if config_int_rows else _ON_CFG(),
+                        _ON_HIST(on_hist) if hist_bins else _ON_HIST(),
+                        _ON_REPL(on_repl) if independent else _ON_REPL())
+    res = (EnsembleResult * T)()
+    tot = EnsembleTotals()
+    rc = lib.hmc_run_program_ensemble(arr, T, int(device), _p(pos), C.byref(opt), C.byref(sink),
+                                      res, C.byref(tot))
+    out = dict(
+        s_bias=np.array([[r.s_bias[i] for i in range(ns)] for r in res]),
+        counts=np.array([[r.config_count[i] for i in range(ns)] for r in res], dtype=np.uint64),
+        rounds=np.array([r.rounds for r in res]), accepted=np.array([bool(r.accepted) for r in res]),
+        err=np.array([r.err_flags for r in res], dtype=np.uint32),
+        formed=np.array([r.formed for r in res], dtype=np.uint64),
+        broken=np.array([r.broken for r in res], dtype=np.uint64),
+        unique_pos=[np.array(r.unique_pos[:nb * 3]).reshape(nb, 3) if r.have_unique else None for r in res],
+        unique_vel=[np.array(r.unique_vel[:nb * 3]).reshape(nb, 3) if r.have_unique else None for r in res],
+        counts_rounds=[np.array(x, dtype=np.uint64).reshape(-1, ns) for x in rounds_log],
+        events=np.array([tot.collisions, tot.cell_crossings], dtype=np.uint64),
+        seconds=tot.seconds, seconds_device=tot.seconds_device, collectives=int(tot.collectives))
+    if dist_rows:
+        out["dist"] = [np.concatenate(d) if d else np.zeros((0, params_list[t].n_nonlocal))
+                       for t, d in enumerate(dist)]
+    if config_int_rows:
+        out["config_int"] = [np.concatenate(c) if c else np.zeros(0, np.uint64) for c in cfg]
+    if hist_bins:
+        out["dist_hist"] = np.stack([h if h is not None else
+                                     np.zeros((max(q.n_nonlocal for q in params_list), 2, hist_bins), np.uint64)
+                                     for h in hist])
+    if independent:
+        out["replicas"] = repl
+    if rc != 0:
+        raise EnsembleError(tot.message.decode() or "hmc_run_program_ensemble failed (%d)" % rc,
+                            results=out, code=rc)
+    return out
+

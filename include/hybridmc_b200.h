@@ -381,6 +381,133 @@ int hmc_h5_attribute(hmc_h5 f, const char *name, int dtype, int rank, const uint
 int hmc_h5_write(hmc_h5 f, const char *filename, int do_fsync);
 int hmc_h5_destroy(hmc_h5 f);
 
+/* ---- multi-GPU: replicas of one transition spread over several ranks ----------------
+ * One process per GPU.  Each rank builds a handle with its share of every transition's
+ * replicas; the only exchange of the path is an integer all-reduce of the per-state
+ * counts (and of the first-passage-time histograms) once per G-test round — SURVEY.md
+ * section 8(e); it replaces the reference's hmc-per-process + files-on-disk hand-off
+ * (tools/init_json.py:14-36) and its planned `hmc_allreduce_counts(h, ncclComm_t)`.
+ * The communicator is the library's own (NCCL loaded with dlopen at first use), so a
+ * C/C++ host needs neither torch nor MPI. */
+#define HMC_COMM_ID_BYTES 128
+typedef struct hmc_comm_s *hmc_comm;
+/* rank 0: make an id and hand its 128 bytes to the other ranks by any means */
+int hmc_comm_unique_id(uint8_t id[HMC_COMM_ID_BYTES]);
+int hmc_comm_create(const uint8_t id[HMC_COMM_ID_BYTES], int rank, int world, int device,
+                    hmc_comm *out);
+/* the same with the id passed through a file all ranks can see (rank 0 writes it) */
+int hmc_comm_create_from_file(const char *path, int rank, int world, int device, hmc_comm *out);
+int hmc_comm_destroy(hmc_comm c);
+int hmc_comm_rank(hmc_comm c);
+int hmc_comm_world(hmc_comm c);
+int hmc_comm_nccl_version(void);
+/* collectives issued through this communicator so far */
+uint64_t hmc_comm_collectives(hmc_comm c);
+/* Sum config_count[T][nstates] over all ranks, in place in the accumulator block,
+ * ordered on the handle's stream (asynchronous; the getters synchronise) — once per
+ * G-test round, after the round's hmc_run and before hmc_get_counts (the counts are
+ * zeroed by hmc_reset_counts at the start of every round).  u64 sums: exact and
+ * order-independent, so every rank then computes the same s_bias update redundantly.
+ * A NULL or 1-rank communicator is a no-op. */
+int hmc_allreduce_counts(hmc_handle h, hmc_comm c);
+/* The running totals behind it (formed[T] ++ broken[T] ++ events[4]) and the distance
+ * histograms (hmc_enable_dist_hist) accumulate over the rounds: sum them ONCE, when the
+ * loop has ended (summing an already summed block again would count it world times). */
+int hmc_allreduce_totals(hmc_handle h, hmc_comm c);
+int hmc_allreduce_hist(hmc_handle h, hmc_comm c);
+/* Host-buffer helpers for the O(states) bookkeeping around it (blocking):
+ * op 0 sum, 1 max, 2 min. */
+int hmc_comm_allreduce_host_u64(hmc_comm c, uint64_t *buf, uint64_t n, int op);
+int hmc_comm_bcast_host(hmc_comm c, void *buf, uint64_t nbytes, int root);
+int hmc_comm_allreduce_device_u64(hmc_comm c, void *dptr, uint64_t n, void *cuda_stream);
+/* RNG identity of the handle's replicas: replica j of transition t draws the Philox
+ * streams of replica  t * total_per_transition + first + j  of the whole (multi-rank)
+ * ensemble, so a split run reproduces the one-rank run bit for bit.  Default: local
+ * indices (first = 0, total = replicas_per_transition). */
+int hmc_set_replica_ids(hmc_handle h, unsigned first, unsigned total_per_transition);
+
+/* ---- independent-program mode ----------------------------------------------------------
+ * Every replica keeps its own s_bias and its own config_count, i.e. runs the reference's
+ * whole program like one CPU process with its own seed (R replicas = R reference seeds
+ * at equal sample counts; the statistical-parity tests use it). */
+/* per-replica counts config_count[R_total][nstates] (zeroed by hmc_reset_counts) */
+int hmc_enable_replica_counts(hmc_handle h, int on);
+int hmc_get_replica_counts(hmc_handle h, uint64_t *config_count);
+/* skip[R_total] != 0: the replica sits out the following hmc_run calls (its program has
+ * finished).  NULL clears the mask. */
+int hmc_set_replica_skip(hmc_handle h, const uint8_t *skip);
+
+/* ---- the ensemble program (production path) ---------------------------------------------
+ * The phase loop of the reference's main (src/main.cc:411-491: equilibrate ->
+ * Wang-Landau -> G-test rounds) for T transitions of one lattice layer, `replicas`
+ * replicas each, on device Philox streams.  Pooled mode: the counts of a transition's
+ * replicas are summed (over all ranks of `comm`) before compute_entropy / g_test, so one
+ * round of `iters_per_round` iterations samples replicas * iters_per_round * nsteps /
+ * write_step configurations.  Independent mode: see above.  Everything but O(T * nstates)
+ * arithmetic and the output hooks runs on the GPU. */
+typedef struct hmc_ensemble_options {
+  uint32_t replicas;        /* per transition, on THIS rank */
+  uint32_t iters_per_round; /* 0: ceil(total_iter / (replicas * world)), at least 1 */
+  uint32_t eq_iters;        /* 0: min(total_iter_eq, 8) */
+  uint32_t max_rounds;      /* 0: max_g_test_count */
+  uint32_t wang_landau;     /* 1: per-replica WL pre-estimate, pooled by its exact mean */
+  uint32_t independent;     /* 1: independent-program mode (no pooling, no comm) */
+  uint32_t hist_bins;       /* >0: pooled distance histograms over [0, hist_rmax) */
+  uint32_t dist_rows;       /* >0: keep this many raw dist rows per transition and round
+                               (replica-major subsample) for the `dist` dataset */
+  uint32_t config_int_rows; /* >0: likewise config/int entries */
+  uint32_t seed0, seed1;    /* Philox key */
+  uint32_t pad;
+  double hist_rmax;
+  hmc_comm comm;            /* NULL: one rank */
+} hmc_ensemble_options;
+
+typedef struct hmc_ensemble_result { /* one per transition */
+  double s_bias[16];
+  uint64_t config_count[16]; /* of the accepting (or last) round */
+  uint64_t formed, broken;
+  uint32_t rounds;
+  int accepted;
+  uint32_t err_flags;        /* OR over the transition's replicas (all ranks) */
+  int have_unique;
+  double unique_pos[HMC_MAX_BEADS * 3]; /* first recorded config == 1 (lowest replica id) */
+  double unique_vel[HMC_MAX_BEADS * 3];
+} hmc_ensemble_result;
+
+typedef struct hmc_ensemble_totals {
+  uint64_t collisions, cell_crossings; /* all ranks */
+  double seconds, seconds_device;      /* wall time of the loop / kernel time of this rank */
+  uint64_t collectives;
+  char message[256];
+} hmc_ensemble_totals;
+
+typedef struct hmc_ensemble_sink {
+  void *user;
+  /* after every round, for every transition that was still running */
+  void (*on_round)(void *user, int transition, unsigned round, const uint64_t *config_count,
+                   const double *s_bias, int nstates, int accepted, double g_val, double g_crit,
+                   double p_val);
+  /* raw samples of the round (options dist_rows / config_int_rows), this rank's replicas */
+  void (*on_dist)(void *user, int transition, const double *rows, unsigned nrows, unsigned nbonds);
+  void (*on_config_int)(void *user, int transition, const uint64_t *config_int, unsigned n);
+  /* once, at the end: pooled histograms hist[n_nonlocal][2][nbins] of the transition */
+  void (*on_hist)(void *user, int transition, const uint64_t *hist, unsigned n_nonlocal,
+                  unsigned nbins);
+  /* independent mode, at the end: s_bias[replicas][nstates], rounds[replicas],
+   * accepted[replicas] of the transition */
+  void (*on_replicas)(void *user, int transition, const double *s_bias, const uint32_t *rounds,
+                      const uint8_t *accepted, unsigned replicas, int nstates);
+} hmc_ensemble_sink;
+
+/* start_pos[T][nbeads][3]: one start structure per transition (init_pos or the previous
+ * layer's unique_config/pos).  res[T].  Returns 0, or <0 with totals->message set; a
+ * replica error flag (reference: uncaught exception) stops the loop after the round in
+ * which it was raised and is reported in res[t].err_flags with return value -8. */
+int hmc_run_program_ensemble(const hmc_params *transitions, int n_transitions, int device,
+                             const double *start_pos, const hmc_ensemble_options *opt,
+                             const hmc_ensemble_sink *sink, hmc_ensemble_result *res,
+                             hmc_ensemble_totals *totals);
+
 /* ---- launch statistics (for bench.py) ------------------------------------ */
 
 /* kernels launched by this handle so far, and the device time (ms, CUDA

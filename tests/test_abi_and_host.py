@@ -29,7 +29,7 @@ def test_header_symbols_exported():
     assert declared == set(eng.EXPORTS), declared ^ set(eng.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.hmc_abi_version() == 1
+    assert lib.hmc_abi_version() == 2
 
 
 def test_params_struct_layout_matches_c():
