@@ -5,14 +5,14 @@ ensemble launch; layer L+1 starts from a structure harvested from layer L in whi
 the new bond is formed (the reference passes it through `unique_config/pos` of the
 previous layer's HDF5 file, src/snapshot.cc:122-131).
 
-Also the per-transition estimator `run_transition_ensemble`: the phase loop of the
-reference's main (src/main.cc:411-491: equilibrate -> Wang-Landau -> G-test loop)
-driven over R replicas with pooled counts.
+The per-transition estimator itself (the phase loop of the reference's main,
+src/main.cc:411-491: equilibrate -> Wang-Landau -> G-test loop, over R replicas with
+pooled counts) is C++: `hmc_run_program_ensemble` in csrc/hmc_program.cu.
 """
 import numpy as np
 
-from .engine import (PHASE_EQ, PHASE_MAIN, PHASE_WL, Engine, compute_entropy, g_test,
-                     init_pos_chain)
+from .engine import (PHASE_EQ, PHASE_MAIN, Engine, compute_entropy, g_test, init_pos_chain,
+                     run_program_ensemble)
 from .params import params_from_json, transition_jsons
 
 
@@ -73,68 +73,21 @@ def harvest_start_structures(master_json, device=0, replicas=128, eq_iters=4, ma
 
 def run_transition_ensemble(params_list, start_pos, replicas, device=0, seed=(1, 2),
                             iters_per_round=None, eq_iters=None, max_rounds=None, wl=True,
-                            hist_bins=0, hist_rmax=0.0, verbose=False):
+                            hist_bins=0, hist_rmax=0.0, verbose=False, comm=None, **kw):
     """The reference's per-transition program (main.cc:411-491) for a batch of
-    transitions of one layer, R replicas each, pooled flat-histogram updates.
+    transitions of one layer, R replicas each (per rank of `comm`), pooled flat-histogram
+    updates: a thin front of the library's C++ phase loop `hmc_run_program_ensemble`
+    (engine.run_program_ensemble), which is the only implementation of it.
 
     Per G-test round every replica runs `iters_per_round` iterations of run_trajectory
-    (default total_iter / R rounded up, so a round pools about as many recorded
-    configurations as one reference iteration ... times R when iters_per_round is
-    given explicitly).  Returns dict(s_bias[T][nstates], rounds, counts, events, err).
-    """
-    p = params_list[0]
-    T = len(params_list)
-    iters = iters_per_round or max(1, -(-p.total_iter // replicas))
-    eq = eq_iters if eq_iters is not None else max(1, min(p.total_iter_eq, 8))
-    cap = max_rounds or p.max_g_test_count
-    with Engine(params_list, replicas, device) as e:
-        pos = np.stack([np.broadcast_to(sp, (replicas,) + sp.shape) for sp in start_pos])
-        e.set_positions(pos.reshape(e.R, e.nb, 3))
-        e.seed(*seed)
-        e.init_config_from_positions()
-        s_bias = np.tile(e.init_s(), (T, 1))
-        if hist_bins:
-            e.enable_dist_hist(hist_bins, hist_rmax)
-        e.reset_clocks()
-        e.run(PHASE_EQ, 0, eq)
-        e.init_config_from_positions()
-        e.reset_clocks()
-        if wl:
-            e.run(PHASE_WL, 0, e.wl_outer_iterations())
-            # pooled Wang-Landau estimate: mean over the replicas of each transition
-            s_bias = e.get_s_bias().reshape(T, replicas, e.nstates).mean(axis=1)
-            e.set_s_bias(s_bias)
-        done = np.zeros(T, dtype=bool)
-        rounds = np.zeros(T, dtype=int)
-        counts = None
-        for rnd in range(cap):
-            e.reset_clocks()
-            e.reset_counts()
-            e.run(PHASE_MAIN, 0, iters)
-            counts, formed, broken, err = e.get_counts()
-            for t in range(T):
-                if done[t]:
-                    continue
-                s_bias[t] = compute_entropy(counts[t], s_bias[t], p.pos_scale, p.neg_scale)
-                rounds[t] += 1
-                ok, g, crit, pv = g_test(counts[t], p.sig_level)
-                if verbose:
-                    print("round", rnd, "transition", t, "s_bias", s_bias[t], "counts", counts[t],
-                          "ACCEPTED" if ok else "REJECTED", g, crit)
-                done[t] = ok
-            e.set_s_bias(s_bias)
-            if done.all():
-                break
-        upos, uvel, found = e.get_unique_config()
-        found = found.reshape(T, replicas).astype(bool)
-        upos = upos.reshape(T, replicas, e.nb, 3)
-        unique = [upos[t, np.nonzero(found[t])[0][0]].copy() if found[t].any() else None
-                  for t in range(T)]
-        out = dict(s_bias=s_bias, rounds=rounds, counts=counts, events=e.get_event_counts(),
-                   err=err, accepted=done, unique_pos=unique, formed=formed, broken=broken)
-        if hist_bins:
-            out["dist_hist"] = e.get_dist_hist()
-        return out
+    (default total_iter / (R * world) rounded up, so that a round pools about as many
+    recorded configurations as one reference round).  Raises engine.EnsembleError when a
+    replica raised an error flag (the reference throws at the same points)."""
+    return run_program_ensemble(params_list, start_pos, replicas, device=device, seed=seed,
+                                iters_per_round=iters_per_round or 0,
+                                eq_iters=eq_iters or 0, max_rounds=max_rounds or 0, wl=wl,
+                                hist_bins=hist_bins, hist_rmax=hist_rmax, verbose=verbose,
+                                comm=comm, **kw)
 
 
 # ---- multi-GPU: one process per GPU, shard + one all-reduce per G-test round ----------

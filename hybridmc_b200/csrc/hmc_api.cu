@@ -21,6 +21,7 @@ struct hmc_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr; // hmc_timer_start / hmc_timer_stop
   bool timing_pending = false;
   float last_ms = 0.f;
   uint64_t n_launches = 0;
@@ -379,6 +380,8 @@ int hmc_create(const hmc_params *tr, int n_transitions, int replicas_per_transit
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
+  CKC(cudaEventCreate(&h->tm0));
+  CKC(cudaEventCreate(&h->tm1));
 
   // tables
   const int nb = h->nb, np = h->npairs;
@@ -472,6 +475,8 @@ int hmc_destroy(hmc_handle h) {
     if (b) cudaFree(b);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->tm0) cudaEventDestroy(h->tm0);
+  if (h->tm1) cudaEventDestroy(h->tm1);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -1072,6 +1077,22 @@ int hmc_get_launch_stats(hmc_handle h, uint64_t *n_launches, float *last_ms) {
   if (n_launches) *n_launches = h->n_launches;
   if (last_ms) *last_ms = h->last_ms;
   return rc;
+}
+
+int hmc_timer_start(hmc_handle h) {
+  if (!h) return fail(h, "null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->tm0, h->stream));
+  return 0;
+}
+
+int hmc_timer_stop(hmc_handle h, float *ms) {
+  if (!h || !ms) return fail(h, "hmc_timer_stop: null");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->tm1, h->stream));
+  CK(cudaEventSynchronize(h->tm1));
+  CK(cudaEventElapsedTime(ms, h->tm0, h->tm1));
+  return 0;
 }
 
 unsigned hmc_wl_outer_iterations(const hmc_params *p) { return wl_outer_iterations(*p); }

@@ -26,6 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libhybridmc_b200.so")
 
 # every symbol include/hybridmc_b200.h declares
 EXPORTS = [
+    "hmc_timer_start", "hmc_timer_stop",
     "hmc_create", "hmc_destroy", "hmc_last_error", "hmc_abi_version",
     "hmc_set_positions", "hmc_get_positions", "hmc_get_velocities", "hmc_set_config",
     "hmc_get_config", "hmc_init_config_from_positions", "hmc_set_s_bias", "hmc_get_s_bias",
@@ -363,6 +364,15 @@ class Engine:
         self._ck(self.lib.hmc_get_launch_stats(self.h, C.byref(n), C.byref(ms)))
         return int(n.value), float(ms.value)
 
+    def timer_start(self):
+        self._ck(self.lib.hmc_timer_start(self.h))
+
+    def timer_stop(self):
+        """ms on the engine's stream since timer_start (kernels, all-reduce, copies, gaps)"""
+        ms = C.c_float()
+        self._ck(self.lib.hmc_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
 
 # ---- entropy.cc mirror (host, O(nstates)) ---------------------------------------
 
@@ -568,13 +578,14 @@ class EnsembleError(EngineError):
 def run_program_ensemble(params_list, start_pos, replicas, device=0, seed=(1, 2),
                          iters_per_round=0, eq_iters=0, max_rounds=0, wl=True,
                          independent=False, hist_bins=0, hist_rmax=0.0, dist_rows=0,
-                         config_int_rows=0, comm=None, verbose=False):
+                         config_int_rows=0, comm=None, verbose=False, keep_rounds=None):
     """hmc_run_program_ensemble: the reference's per-transition program (main.cc:411-491)
     for T transitions of one layer x `replicas` replicas each on THIS rank, pooled over the
     ranks of `comm`.  Returns a dict: s_bias[T][nstates], rounds[T], accepted[T], counts[T],
     counts_rounds (per transition: the config_count row of every round), err[T], formed,
     broken, unique_pos/unique_vel (list, None where no bonded structure was recorded),
-    dist / config_int (lists of arrays, when requested), dist_hist[T][n_nonlocal][2][bins],
+    dist / config_int (lists of arrays, when requested; the rows of the last `keep_rounds`
+    rounds, all by default), dist_hist[T][n_nonlocal][2][bins],
     replicas (independent mode: per transition (s_bias[R][ns], rounds[R], accepted[R])),
     events (collisions, cell crossings), seconds, seconds_device, collectives."""
     lib = load_library()
@@ -605,9 +616,13 @@ def run_program_ensemble(params_list, start_pos, replicas, device=0, seed=(1, 2)
 
     def on_dist(_u, t, rows, n, nbonds):
         dist[t].append(np.ctypeslib.as_array(rows, shape=(n, nbonds)).copy())
+        if keep_rounds and len(dist[t]) > keep_rounds:
+            del dist[t][0]
 
     def on_cfg(_u, t, vals, n):
         cfg[t].append(np.ctypeslib.as_array(vals, shape=(n,)).copy())
+        if keep_rounds and len(cfg[t]) > keep_rounds:
+            del cfg[t][0]
 
     def on_hist(_u, t, h, nl, nbins):
         hist[t] = np.ctypeslib.as_array(h, shape=(nl, 2, nbins)).copy()

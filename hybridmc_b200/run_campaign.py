@@ -14,9 +14,13 @@ tools/init_json.py:174-183), writing into the current directory as init_json.py 
 the reference's `tools/run.py master.json <exe> <this file>` drives it unchanged (`exe`
 and `--nproc` are accepted and unused: the transitions run inside this process).
 
-Multi-GPU: launch one process per GPU (torchrun); the transitions of a layer are dealt
-round-robin to the ranks (campaign.shard) and the harvested start structures of the next
-layer are exchanged with one all-gather per layer.
+Multi-GPU: launch one process per GPU (torchrun).  Every rank runs ALL transitions of the
+layer with `replicas / world` replicas each (the replicas of one transition span the
+GPUs, so a 10-transition layer loads 8 GPUs as evenly as a 1260-transition one); the ranks
+meet in ONE NCCL all-reduce of the per-state counts per G-test round (library
+communicator, `hmc_allreduce_counts`), compute the identical s_bias update redundantly, and
+rank 0 writes the files.  The start structures need no exchange: every rank receives the
+same `unique_config` row from the program.
 """
 import argparse
 import csv
@@ -32,8 +36,8 @@ if __package__ in (None, ""):  # started by path, the way tools/run.py starts in
     import hybridmc_b200  # noqa: F401
     __package__ = "hybridmc_b200"
 
-from .campaign import layers_of, run_transition_ensemble, shard
-from .engine import init_pos_chain
+from .campaign import layers_of, run_transition_ensemble
+from .engine import Comm, EnsembleError, init_pos_chain
 from .output import File, write_hdf5
 from .params import transition_jsons
 
@@ -64,12 +68,26 @@ def stair_stages(d, layer, master_rc, stair_rc):
     return out
 
 
+def layer_replicas(replicas, n_transitions, world=1, fill=0):
+    """Replicas per transition on ONE rank.  `replicas` is the total per transition over all
+    ranks; with fill > 0 thin layers are topped up until about `fill` replicas run per GPU
+    (a 10-transition layer would otherwise leave most of the 148 SMs idle; the rounds get
+    proportionally shorter because iterations per round = total_iter / replicas)."""
+    per_rank = -(-replicas // world)
+    if fill and n_transitions * per_rank < fill:
+        per_rank = -(-fill // n_transitions)
+    return per_rank
+
+
 def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, max_rounds=40,
                  max_layers=None, hist_bins=2048, rank=0, world=1, log=print, wl=True,
-                 eq_iters=None, seed_increment=1, stair_bp=None, stair_rc=None):
+                 eq_iters=None, seed_increment=1, stair_bp=None, stair_rc=None, comm=None,
+                 fill=0, dist_rows=None, config_int_rows=None, keep_rounds=4):
     """stair_bp / stair_rc: init_json.py's --bp / --rc — the transitions that form bond
     `stair_bp` run as a sequence of stages with shrinking rc, each started from the previous
-    stage's structure; stage j of all of a layer's staircase transitions is one ensemble."""
+    stage's structure; stage j of all of a layer's staircase transitions is one ensemble.
+    `replicas`: per transition, summed over the ranks of `comm`.
+    Returns (summary rows, seconds, collision events)."""
     from .params import params_from_json
     os.makedirs(out_dir, exist_ok=True)
     layers = layers_of(master, seed_increment)
@@ -79,11 +97,12 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
     rmax = master["length"] * 0.5 * 3 ** 0.5
     stair_bp = sorted(stair_bp) if stair_bp is not None else None
     summary = []
+    events = 0
     t_start = time.time()
     for layer, trans in layers:
         if max_layers is not None and layer >= max_layers:
             break
-        mine = shard(len(trans), rank, world)
+        mine = list(range(len(trans)))
         # jobs[k] = the stages of transition k: [(params, json, output name)]
         jobs = {}
         for k in mine:
@@ -112,38 +131,40 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                             new_structs.setdefault(trans[k][1], stage_pos[k])
                 else:
                     todo.append(k)
+            if world > 1:  # every rank must see the same list (rank 0 may already have written)
+                todo = [int(k) for k in comm.bcast(np.array(
+                    todo + [-1] * (len(mine) - len(todo)), dtype=np.int64)) if k >= 0]
             if not todo:
                 continue
             params = [jobs[k][stage][0] for k in todo]
+            p0 = params[0]
+            R = layer_replicas(replicas, len(todo), world, fill)
+            # raw rows kept per transition and round (the reference: total_iter * nsteps per
+            # round, all rounds; here bounded — the pooled dist_hist is the full statistic)
+            rows = min(p0.total_iter * p0.nsteps, 4096) if dist_rows is None else dist_rows
+            cfgs = (min(p0.total_iter * (p0.nsteps // max(p0.write_step, 1) + p0.mc_write + 1), 4096)
+                    if config_int_rows is None else config_int_rows)
             t0 = time.time()
-            out = run_transition_ensemble(params, [stage_pos[k] for k in todo], replicas,
-                                          device=device, seed=(params[0].seeds[0], 1 + layer + 64 * stage),
-                                          iters_per_round=iters_per_round, max_rounds=max_rounds,
-                                          hist_bins=hist_bins, hist_rmax=rmax, wl=wl,
-                                          eq_iters=eq_iters)
+            try:
+                out = run_transition_ensemble(
+                    params, [stage_pos[k] for k in todo], R, device=device,
+                    seed=(p0.seeds[0], 1 + layer + 64 * stage), iters_per_round=iters_per_round,
+                    max_rounds=max_rounds, hist_bins=hist_bins, hist_rmax=rmax, wl=wl,
+                    eq_iters=eq_iters, comm=comm, dist_rows=rows, config_int_rows=cfgs,
+                    keep_rounds=keep_rounds)
+            except EnsembleError as ex:
+                # the reference's process dies with an exception here (main.cc:48-56,219-225):
+                # nothing of this batch is written as valid output
+                bad = [jobs[k][stage][2] for n, k in enumerate(todo)
+                       if ex.results is not None and ex.results["err"][n] & ~np.uint32(32)]
+                log("layer %d: replica error flags in %s" % (layer, bad))
+                raise
             dt = time.time() - t0
+            events += int(out["events"][0])
             for n, k in enumerate(todo):
                 bits_in, bits_out, _ = trans[k]
                 p, dj, name = jobs[k][stage]
-                with open(os.path.join(out_dir, name + ".json"), "w") as f:
-                    json.dump(dj, f)
                 up = out["unique_pos"][n]
-                ds = {"s_bias": out["s_bias"][n].astype(np.float32),  # f32 as main.cc:445-446
-                      "config_count": np.vstack([np.zeros(2, np.uint64), out["counts"][n]]),
-                      "dist_hist": out["dist_hist"][n],
-                      "unique_config/pos": (up[None] if up is not None
-                                            else np.zeros((0, p.nbeads, 3)))}
-                at = {"sigma": np.float64(p.sigma), "length": np.float64(p.length),
-                      "nsteps": np.uint32(p.nsteps), "dist_hist_rmax": np.float64(rmax),
-                      "nonlocal_bonds": np.array(p.bond_list("nonlocal"), np.uint32).reshape(-1, 2),
-                      "transient_bonds": np.array(p.bond_list("transient"), np.uint32).reshape(-1, 2),
-                      "permanent_bonds": np.array(p.bond_list("permanent"), np.uint32).reshape(-1, 2)}
-                write_output(os.path.join(out_dir, name + ".h5"), ds, at)
-                with open(os.path.join(out_dir, name + ".log"), "w") as f:
-                    f.write("replicas %d rounds %d accepted %s s_bias %s counts %s\n" % (
-                        replicas, out["rounds"][n], bool(out["accepted"][n]),
-                        out["s_bias"][n].tolist(), out["counts"][n].tolist()))
-                # one row per run; a stair stage carries its rc like its file name does
                 summary.append((fmt(bits_in), name.split("_", 3)[3], float(out["s_bias"][n][0])))
                 if up is not None:
                     stage_pos[k] = up
@@ -151,17 +172,46 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                         new_structs.setdefault(bits_out, up)
                 elif stage < len(jobs[k]) - 1:
                     raise RuntimeError("%s: no bonded structure to start the next stair stage from" % name)
-            log("layer %d%s: %d transitions, %d replicas each, rounds %s, %.1f s, events %d, err %d" % (
-                layer, " stage %d" % stage if stage else "", len(todo), replicas,
-                out["rounds"].tolist(), dt, int(out["events"][0]),
-                int(np.bitwise_or.reduce(out["err"]))))
-        if world > 1:
-            import torch.distributed as dist
-            gathered = [None] * world
-            dist.all_gather_object(gathered, new_structs)
-            for g in gathered:
-                for b_, v in g.items():
-                    new_structs.setdefault(b_, v)
+                if rank != 0:
+                    continue
+                with open(os.path.join(out_dir, name + ".json"), "w") as f:
+                    json.dump(dj, f)
+                uv = out["unique_vel"][n]
+                cr = out["counts_rounds"][n]
+                nl = max(p.n_nonlocal, 1)
+                ds = {"s_bias": out["s_bias"][n].astype(np.float32),  # f32 as main.cc:445-446
+                      # ConfigCountWriter: a zero row, then one row per G-test round
+                      # (main.cc:394,488)
+                      "config_count": np.vstack([np.zeros((1, p.nstates), np.uint64),
+                                                 cr if len(cr) else out["counts"][n][None]]),
+                      # per-MD-step bond distances of the last rounds (main.cc:199-200); what
+                      # tools/mfpt.py:76-77 reads
+                      "dist": out["dist"][n].reshape(-1, nl),
+                      "config/int": out["config_int"][n],
+                      "dist_hist": out["dist_hist"][n],
+                      "unique_config/pos": (up[None] if up is not None
+                                            else np.zeros((0, p.nbeads, 3))),
+                      "unique_config/vel": (uv[None] if uv is not None
+                                            else np.zeros((0, p.nbeads, 3))),
+                      "unique_config/config": np.ones(1 if up is not None else 0, np.uint64)}
+                at = {"sigma": np.float64(p.sigma), "length": np.float64(p.length),
+                      "nsteps": np.uint32(p.nsteps), "dist_hist_rmax": np.float64(rmax),
+                      "replicas": np.uint32(R * world), "err_flags": np.uint32(out["err"][n]),
+                      "nonlocal_bonds": np.array(p.bond_list("nonlocal"), np.uint32).reshape(-1, 2),
+                      "transient_bonds": np.array(p.bond_list("transient"), np.uint32).reshape(-1, 2),
+                      "permanent_bonds": np.array(p.bond_list("permanent"), np.uint32).reshape(-1, 2)}
+                write_output(os.path.join(out_dir, name + ".h5"), ds, at)
+                with open(os.path.join(out_dir, name + ".log"), "w") as f:
+                    f.write("replicas %d rounds %d accepted %s s_bias %s counts %s err_flags %d\n" % (
+                        R * world, out["rounds"][n], bool(out["accepted"][n]),
+                        out["s_bias"][n].tolist(), out["counts"][n].tolist(), int(out["err"][n])))
+            if rank == 0:
+                log("layer %d%s: %d transitions, %d replicas each%s, rounds %s, %.1f s (%.1f s device), "
+                    "events %d, collectives %d" % (
+                        layer, " stage %d" % stage if stage else "", len(todo), R * world,
+                        " over %d ranks" % world if world > 1 else "",
+                        _brief(out["rounds"]), dt, out["seconds_device"], int(out["events"][0]),
+                        out["collectives"]))
         for b_, v in new_structs.items():
             structures.setdefault(b_, v)
         missing = [t[1] for lt in layers[layer + 1:layer + 2] for t in lt[1] if t[0] not in structures]
@@ -170,7 +220,12 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
     if rank == 0:
         with open(os.path.join(out_dir, "diff_s_bias.csv"), "a", newline="") as f:
             csv.writer(f).writerows(summary)  # tools/diff_s_bias.py:72-74
-    return summary, time.time() - t_start
+    return summary, time.time() - t_start, events
+
+
+def _brief(rounds):
+    r = np.asarray(rounds)
+    return r.tolist() if len(r) <= 12 else "min %d median %d max %d" % (r.min(), np.median(r), r.max())
 
 
 def main(argv=None):
@@ -184,7 +239,10 @@ def main(argv=None):
     ap.add_argument("--rc", nargs="+", type=float, help="list of rc if potential is step")
     ap.add_argument("--bp", nargs=2, type=int, help="bead pair whose potential is step")
     ap.add_argument("--out", default=None, help="output directory (default: <json name>)")
-    ap.add_argument("--replicas", type=int, default=512)
+    ap.add_argument("--replicas", type=int, default=512,
+                    help="replicas per transition (in total over all ranks)")
+    ap.add_argument("--fill", type=int, default=0,
+                    help="top thin layers up to about this many replicas per GPU")
     ap.add_argument("--device", type=int, default=None)
     ap.add_argument("--iters-per-round", type=int, default=None)
     ap.add_argument("--max-rounds", type=int, default=40)
@@ -200,18 +258,26 @@ def main(argv=None):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     device = args.device if args.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
+    comm = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("gloo")  # host-side hand-off of structures only
+        dist.init_process_group("gloo")  # passes the 128-byte NCCL id around, nothing else
+        comm = Comm.from_torch(device)
     # invoked the way tools/run.py invokes init_json.py: outputs go to the current directory
     out_dir = args.out or ("." if args.exe is not None else
                            os.path.splitext(os.path.basename(args.json))[0])
-    summary, wall = run_campaign(master, out_dir, args.replicas, device, args.iters_per_round,
-                                 args.max_rounds, args.max_layers, hist_bins=args.hist_bins, rank=rank,
-                                 world=world, wl=not args.no_wl, eq_iters=args.eq_iters,
-                                 seed_increment=args.seed_increment, stair_bp=args.bp, stair_rc=args.rc)
-    print("rank %d: %d transitions in %.1f s -> %.0f transitions/hour" % (
-        rank, len(summary), wall, 3600.0 * len(summary) / max(wall, 1e-9)))
+    summary, wall, events = run_campaign(
+        master, out_dir, args.replicas, device, args.iters_per_round, args.max_rounds,
+        args.max_layers, hist_bins=args.hist_bins, rank=rank, world=world, wl=not args.no_wl,
+        eq_iters=args.eq_iters, seed_increment=args.seed_increment, stair_bp=args.bp,
+        stair_rc=args.rc, comm=comm, fill=args.fill)
+    if rank == 0:
+        print("%d transitions on %d GPU(s) in %.1f s -> %.0f transitions/hour, %.3e collision "
+              "events (%.3e events/s whole campaign)" % (
+                  len(summary), world, wall, 3600.0 * len(summary) / max(wall, 1e-9), events,
+                  events / max(wall, 1e-9)))
+    if comm is not None:
+        comm.close()
 
 
 if __name__ == "__main__":

@@ -513,6 +513,11 @@ int hmc_run_program_ensemble(const hmc_params *transitions, int n_transitions, i
 /* kernels launched by this handle so far, and the device time (ms, CUDA
  * events on the handle's stream) of the last hmc_run / injected call. */
 int hmc_get_launch_stats(hmc_handle h, uint64_t *n_launches, float *last_ms);
+/* Interval timer on the handle's stream (CUDA events): everything enqueued between the two
+ * calls — kernels, the NCCL all-reduce of hmc_allreduce_counts, copies — and the host gaps
+ * between them.  hmc_timer_stop synchronises and returns the milliseconds. */
+int hmc_timer_start(hmc_handle h);
+int hmc_timer_stop(hmc_handle h, float *ms);
 
 #ifdef __cplusplus
 }

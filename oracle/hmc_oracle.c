@@ -1493,3 +1493,69 @@ int orc_run_main(const hmc_params *p, const double *pos_in, unsigned max_gtest_i
   orc_destroy(s);
   return err ? -1 : 0;
 }
+
+/* The oracle's replay of oracle/ref_driver.cc:ref_bench_main_phase (bench.py's CPU leg):
+ * the same call sequence, bit-identical trajectory, and the event counters the reference
+ * does not have.  collisions / cell_crossings count the timed part only. */
+int orc_bench_main_phase(const hmc_params *p, const double *pos_in, unsigned eq_iters,
+                         unsigned rounds, unsigned iters_per_round, double *seconds,
+                         double *pos_final, uint64_t *config_final, uint64_t *collisions,
+                         uint64_t *cell_crossings) {
+  orc_sim *s = orc_create(p);
+  const unsigned nb = p->nbeads, ns = s->nstates;
+  orc_mt19937 g;
+  orc_mt_seed_seq(&g, p->seeds, p->n_seeds);
+  const double vsig = sqrt(p->temp / p->m);
+  double *normals = (double *)malloc(sizeof(double) * 3 * nb);
+  int err = 0;
+  orc_reset_clocks(s);
+  orc_set_pos(s, pos_in);
+  orc_init_config_from_pos(s);
+  orc_init_s(s);
+  for (unsigned iter = 0; !err && iter < eq_iters; iter++)
+    for (unsigned step = iter * p->nsteps_eq; step < (iter + 1) * p->nsteps_eq; step++) {
+      orc_mt_normals(&g, vsig, normals, 3 * nb);
+      err |= orc_md_step(s, HMC_PHASE_EQ, step, normals);
+    }
+  orc_init_config_from_pos(s);
+  const unsigned tape_n = 2048;
+  uint32_t *words = (uint32_t *)malloc(sizeof(uint32_t) * tape_n);
+  double *st = (double *)malloc(sizeof(double) * tape_n);
+  double *ct = (double *)malloc(sizeof(double) * tape_n);
+  const uint64_t c0 = s->n_coll, x0 = s->n_cell;
+  const double t0 = now_s();
+  for (unsigned r = 0; !err && r < rounds; r++) {
+    orc_reset_clocks(s);
+    memset(s->config_count, 0, sizeof(uint64_t) * ns);
+    for (unsigned iter = 0; !err && iter < iters_per_round; iter++) {
+      for (unsigned step = iter * p->nsteps; step < (iter + 1) * p->nsteps; step++) {
+        orc_mt_normals(&g, vsig, normals, 3 * nb);
+        err |= orc_md_step(s, HMC_PHASE_MAIN, step, normals);
+      }
+      unsigned done = 0;
+      while (!err && done < p->mc_moves) {
+        orc_mt_tape(&g, words, st, ct, tape_n);
+        unsigned cursor = 0;
+        const int e2 = orc_crankshaft(s, done, p->mc_moves - done, words, st, ct, tape_n, &cursor);
+        if ((e2 & HMC_ERR_TAPE_UNDERRUN) && s->last_moves_done == 0) {
+          err |= e2;
+          break;
+        }
+        orc_mt_discard(&g, cursor);
+        done += s->last_moves_done;
+      }
+    }
+    orc_compute_entropy(s->config_count, s->s_bias, (int)ns, p->pos_scale, p->neg_scale);
+  }
+  *seconds = now_s() - t0;
+  *collisions = s->n_coll - c0;
+  *cell_crossings = s->n_cell - x0;
+  memcpy(pos_final, s->pos, sizeof(double) * 3 * nb);
+  *config_final = orc_get_config(s);
+  free(words);
+  free(st);
+  free(ct);
+  free(normals);
+  orc_destroy(s);
+  return err ? -1 : 0;
+}

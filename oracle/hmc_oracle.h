@@ -136,6 +136,12 @@ int orc_run_main(const hmc_params *p, const double *pos_in,
                  double *dist_out, unsigned *n_dist_rows,
                  orc_main_result *res);
 
+/* bench.py's CPU leg: see hmc_oracle.c / ref_driver.cc:ref_bench_main_phase */
+int orc_bench_main_phase(const hmc_params *p, const double *pos_in, unsigned eq_iters,
+                         unsigned rounds, unsigned iters_per_round, double *seconds,
+                         double *pos_final, uint64_t *config_final, uint64_t *collisions,
+                         uint64_t *cell_crossings);
+
 #ifdef __cplusplus
 }
 #endif

@@ -497,6 +497,86 @@ int ref_run_main(const hmc_params *h, const double *pos_in, unsigned max_gtest_i
   return rc;
 }
 
+// CPU-baseline leg of bench.py (same workload as the GPU arm): the reference's OWN
+// run_trajectory (main.cc:171-247: nsteps MD intervals with fresh velocities, mc_moves
+// crankshaft moves, sampling) called `rounds` x `iters_per_round` times from a given start
+// structure, compute_entropy after every round as the G-test loop does (main.cc:451-491).
+// `eq_iters` iterations of run_trajectory_eq come first, untimed.  Only calls into
+// unmodified reference functions are timed; the reference has no event counter, so the
+// number of events of this (deterministic) run comes from the oracle's bit-identical
+// replay orc_bench_main_phase (tests/test_oracle_vs_ref.py pins the two on pos_final).
+int ref_bench_main_phase(const hmc_params *h, const double *pos_in, unsigned eq_iters,
+                         unsigned rounds, unsigned iters_per_round, double *seconds,
+                         double *pos_final, uint64_t *config_final) {
+  std::stringstream sink;
+  auto *old = std::cout.rdbuf(sink.rdbuf());
+  int rc = 0;
+  try {
+    const Param p = to_param(*h);
+    Param p_eq = p;
+    const Box box{p.length};
+    UpdateConfig update_config;
+    const unsigned t_bonds = p.transient_bonds.get_nbonds();
+    const unsigned nbonds = p.nonlocal_bonds.get_nbonds();
+    const unsigned nstates = std::pow(2, t_bonds);
+    ConfigInt store_config_int;
+    std::vector<uint64_t> config_count(nstates);
+    std::vector<double> dist(nbonds);
+    CountBond count_bond = {};
+    System sys(p.nbeads);
+    std::seed_seq seq(p.seeds.begin(), p.seeds.end());
+    Random mt(seq);
+    H5::H5File file("unused", H5F_ACC_TRUNC);
+    UpdateConfigWriter update_config_writer(file);
+    H5::Group group{file.createGroup("unique_config")};
+    PosWriter pos_writer{group, "pos", p.nbeads};
+    VelWriter vel_writer{group, "vel", p.nbeads};
+    ConfigWriter config_writer{group, "config"};
+    DistWriter dist_writer{file, "dist", nbonds};
+    std::set<Config> store_config;
+    for (unsigned i = 0; i < p.nbeads; i++) {
+      sys.times[i] = 0.0;
+      sys.counter[i] = 0.0;
+    }
+    double wall_time = 0.0;
+    UpdateConfig update_config_eq;
+    p_eq.nsteps = p.nsteps_eq;
+    p_eq.total_iter = eq_iters;
+    for (unsigned i = 0; i < p.nbeads; i++)
+      sys.pos[i] = Vec3(pos_in[3 * i], pos_in[3 * i + 1], pos_in[3 * i + 2]);
+    init_update_config(sys.pos, update_config_eq, box, p.rc2, p.transient_bonds);
+    init_s(sys.s_bias, t_bonds);
+    for (unsigned iter = 0; iter < eq_iters; iter++)
+      run_trajectory_eq(sys, mt, p_eq, box, update_config_eq, count_bond, wall_time, iter);
+    init_update_config(sys.pos, update_config, box, p.rc2, p.transient_bonds);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned r = 0; r < rounds; r++) {
+      for (unsigned i = 0; i < p.nbeads; i++) {
+        sys.times[i] = 0.0;
+        sys.counter[i] = 0.0;
+      }
+      wall_time = 0.0;
+      store_config_int.clear();
+      std::fill(config_count.begin(), config_count.end(), 0);
+      for (unsigned iter = 0; iter < iters_per_round; iter++)
+        run_trajectory(sys, mt, p, box, dist, update_config, update_config_writer,
+                       pos_writer, vel_writer, config_writer, dist_writer, store_config,
+                       store_config_int, count_bond, wall_time, iter);
+      for (unsigned i = 0; i < store_config_int.size(); i++)
+        config_count[store_config_int[i]]++;
+      compute_entropy(config_count, sys.s_bias, nstates, p.pos_scale, p.neg_scale);
+    }
+    *seconds =
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::memcpy(pos_final, sys.pos.data(), sizeof(double) * 3 * p.nbeads);
+    *config_final = update_config.config;
+  } catch (const std::exception &e) {
+    rc = -1;
+  }
+  std::cout.rdbuf(old);
+  return rc;
+}
+
 // CPU-baseline leg: time `n_steps` MD steps (initialize_system + run_step via the
 // traced loop, velocities from the sim's engine) and return valid collisions.
 double ref_time_md(ref_sim *s, unsigned first_step, unsigned n_steps, uint64_t *collisions,

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 def test_two_layers_of_test_json(tmp_path):
     master = load_config("test")
     out = str(tmp_path / "camp")
-    summary, seconds = run_campaign(master, out, replicas=48, iters_per_round=2, max_rounds=2,
+    summary, seconds, events = run_campaign(master, out, replicas=48, iters_per_round=2, max_rounds=2,
                                     max_layers=2, hist_bins=2048, wl=False, eq_iters=2,
                                     log=lambda *a: None)
     names = sorted(f for f in os.listdir(out) if f.endswith(".h5"))
@@ -33,7 +33,18 @@ def test_two_layers_of_test_json(tmp_path):
             assert f["s_bias"].dtype == np.float32 and f["s_bias"].shape == (2,)
             assert np.isfinite(f["s_bias"]).all()
             cc = f["config_count"]
-            assert cc.dtype == np.uint64 and cc.shape == (2, 2) and not cc[0].any() and cc[1].all()
+            # a zero row, then one row per G-test round (main.cc:394,488)
+            assert cc.dtype == np.uint64 and cc.shape in ((2, 2), (3, 2))
+            assert not cc[0].any() and cc[1:].all()
+            # what tools/mfpt.py:76-77 and tools/get_error_s_bias.py read
+            nl = len(f.attrs["nonlocal_bonds"])
+            assert f["dist"].ndim == 2 and f["dist"].shape[1] == nl and len(f["dist"]) > 0
+            assert (f["dist"] > 0).all() and (f["dist"] < master["length"]).all()
+            ci = f["config"]["int"]
+            assert ci.dtype == np.uint64 and len(ci) > 0 and set(np.unique(ci)) <= {0, 1}
+            assert f["unique_config"]["vel"].shape == f["unique_config"]["pos"].shape
+            assert len(f["unique_config"]["config"]) == len(f["unique_config"]["pos"])
+            assert int(f.attrs["err_flags"]) & ~32 == 0 and int(f.attrs["replicas"]) == 48
             assert f["dist_hist"].shape[-2:] == (2, 2048)
             assert f["unique_config"]["pos"].shape[1:] == (nb, 3)
             assert f.attrs["nsteps"] == master["nsteps"]
@@ -47,10 +58,16 @@ def test_two_layers_of_test_json(tmp_path):
             p = params_from_json(json.load(jf))
         inner, outer = mfpt.transition_fpts(f["dist_hist"], float(f.attrs["dist_hist_rmax"]), p)
         assert np.isfinite(inner) and 0 < inner < 1 and outer > 0
+        # ... and, like tools/mfpt.py, on the raw `dist` rows of the same file
+        t = p.bond_list("transient")[0]
+        col = [tuple(b) for b in p.bond_list("nonlocal")].index(tuple(t))
+        d = f["dist"][:, col]
+        assert ((d > p.rh * 0.99) & (d < master["length"])).all()
+    assert events > 0
     with open(os.path.join(out, "diff_s_bias.csv")) as f:
         assert len(list(csv.reader(f))) == 9
     # finished transitions are skipped on a second pass (tools/init_json.py:141-142)
-    summary2, _ = run_campaign(master, out, replicas=48, iters_per_round=2, max_rounds=2,
+    summary2, _, _ = run_campaign(master, out, replicas=48, iters_per_round=2, max_rounds=2,
                                max_layers=2, hist_bins=2048, wl=False, eq_iters=2,
                                log=lambda *a: None)
     assert summary2 == []
@@ -64,7 +81,7 @@ def test_staircase_sweep_layer0(tmp_path):
     bonds = sorted(sorted(b) for b in master["nonlocal_bonds"])
     bp = bonds[0]
     out = str(tmp_path / "stair")
-    summary, _ = run_campaign(master, out, replicas=48, iters_per_round=2, max_rounds=2,
+    summary, _, _ = run_campaign(master, out, replicas=48, iters_per_round=2, max_rounds=2,
                               max_layers=1, hist_bins=512, wl=False, eq_iters=2,
                               log=lambda *a: None, stair_bp=bp, stair_rc=[3.0, 2.2, 1.5])
     names = sorted(f[:-3] for f in os.listdir(out) if f.endswith(".h5"))

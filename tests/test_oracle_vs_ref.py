@@ -99,3 +99,33 @@ def test_reference_unit_tests_pass():
     res = subprocess.run([exe], capture_output=True, text=True, cwd="/tmp")
     assert res.returncode == 0, res.stdout[-2000:]
     assert "cases 22" in res.stdout and "failures 0" in res.stdout
+
+
+@pytest.mark.parametrize("index", [1, 4, 9])
+def test_bench_main_phase_replay_is_the_reference_run(oracle, reflib, index):
+    """bench.py's CPU leg times the reference's own run_trajectory calls
+    (ref_bench_main_phase) and takes the event count of that run from the oracle's replay
+    (orc_bench_main_phase): the two must be the same trajectory, bit for bit, from the
+    committed start structures of every lattice layer."""
+    import os
+    from hybridmc_b200.params import transition_jsons
+    master = load_config("test")
+    layer, bits_in, bits_out, d = transition_jsons(master)[index]
+    st = np.load(os.path.join(os.path.dirname(__file__), "golden", "start_structures_test.npz"))
+    start = np.ascontiguousarray(st["".join("1" if b else "0" for b in bits_in)])
+    p = params_from_json(dict(d, seeds=[77 + index, 1]))
+    out = []
+    for lib, fn in ((reflib, "ref_bench_main_phase"), (oracle, "orc_bench_main_phase")):
+        sec, cfg = C.c_double(), C.c_uint64()
+        pos = np.zeros((p.nbeads, 3))
+        extra = []
+        if fn.startswith("orc"):
+            coll, cells = C.c_uint64(), C.c_uint64()
+            extra = [C.byref(coll), C.byref(cells)]
+        rc = getattr(lib, fn)(C.byref(p), start.ctypes.data_as(C.c_void_p), C.c_uint(1), C.c_uint(2),
+                              C.c_uint(2), C.byref(sec), pos.ctypes.data_as(C.c_void_p),
+                              C.byref(cfg), *extra)
+        assert rc == 0
+        out.append((pos, cfg.value))
+    assert np.array_equal(bits(out[0][0]), bits(out[1][0])) and out[0][1] == out[1][1]
+    assert coll.value > 4 * 8 * 1000 and cells.value > 0
