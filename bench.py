@@ -286,8 +286,9 @@ def run_gpu_arm(args):
         """one round of the production loop; returns (ms of the whole step on the engine's
         stream, ms of the kernel alone)"""
         e.timer_start()
+        e.reset_clocks()  # every round starts at step 0, as the G-test loop does (main.cc:453-460)
         e.reset_counts()
-        e.run(PHASE_MAIN, it, 1)
+        e.run(PHASE_MAIN, 0, 1)
         e.allreduce_counts(comm)  # the path's one exchange, on the engine's stream
         cc, _, _, _ = e.get_counts()
         for t in range(e.T):
@@ -346,8 +347,9 @@ def run_gpu_arm(args):
         e.set_positions(host_pos)
         e.set_config(host_cfg)
         e.set_s_bias(s_bias)
+        e.reset_clocks()
         e.reset_counts()
-        e.run(PHASE_MAIN, it, 1)
+        e.run(PHASE_MAIN, 0, 1)
         e.allreduce_counts(comm)
         it += 1
         host_pos[...] = e.get_positions()
