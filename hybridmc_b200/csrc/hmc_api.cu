@@ -1079,6 +1079,16 @@ int hmc_get_launch_stats(hmc_handle h, uint64_t *n_launches, float *last_ms) {
   return rc;
 }
 
+int hmc_resident_replicas(unsigned nbeads, int device) {
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  // 16 warps per SM (the kernel's register budget), 32 / G replicas per warp
+  return sms * 16 * (32 / hmc_pick_group(int(nbeads)));
+}
+
 int hmc_timer_start(hmc_handle h) {
   if (!h) return fail(h, "null handle");
   CK(cudaSetDevice(h->device));

@@ -378,7 +378,9 @@ extern "C" int hmc_run_program_ensemble(const hmc_params *tr, int T, int device,
   std::vector<double> sb(size_t(T) * ns); // pooled mode: one row per transition
   for (int t = 0; t < T; t++)
     for (unsigned i = 0; i < ns; i++) // init_s, entropy.cc:14-20
-      sb[size_t(t) * ns + i] = 3 * (p.n_transient - unsigned(__builtin_popcount(i)));
+      sb[size_t(t) * ns + i] = opt->start_s_bias
+                                   ? opt->start_s_bias[size_t(t) * 16 + i]
+                                   : 3 * (p.n_transient - unsigned(__builtin_popcount(i)));
   ERUN(hmc_set_s_bias(h, sb.data(), int(ns)));
   if (opt->hist_bins) ERUN(hmc_enable_dist_hist(h, opt->hist_bins, opt->hist_rmax));
   if (opt->independent) ERUN(hmc_enable_replica_counts(h, 1));
@@ -419,23 +421,38 @@ extern "C" int hmc_run_program_ensemble(const hmc_params *tr, int T, int device,
   std::vector<double> sb_rep(Rl * ns);
   if (opt->wang_landau) {
     const unsigned nwl = wl_iters(p);
+    // pooled mode: replicas whose global id is a multiple of `stride` take part
+    const unsigned total = R * world;
+    const unsigned stride = (!opt->independent && opt->wl_replicas && opt->wl_replicas < total)
+                                ? total / opt->wl_replicas : 1u;
+    std::vector<uint8_t> wait(Rl, 0);
+    if (stride > 1) {
+      for (size_t r = 0; r < Rl; r++) wait[r] = ((rank * R + unsigned(r % R)) % stride) != 0;
+      ERUN(hmc_set_replica_skip(h, wait.data()));
+    }
     if (nwl) {
       ERUN(hmc_run(h, HMC_PHASE_WL, 0, nwl));
       ERUN(hmc_sync(h));
       add_ms();
     }
+    if (stride > 1) ERUN(hmc_set_replica_skip(h, nullptr));
     ERUN(hmc_get_s_bias(h, sb_rep.data(), int(ns)));
     if (!opt->independent) {
-      // pooled start value: the mean over all replicas of the transition, formed from
-      // exact fixed-point sums (2^-32 resolution) so that it does not depend on how the
-      // replicas are spread over ranks
-      std::vector<uint64_t> fx(size_t(T) * ns, 0);
-      for (size_t r = 0; r < Rl; r++)
+      // pooled start value: the mean over the participating replicas of the transition,
+      // formed from exact fixed-point sums (2^-32 resolution) so that it does not depend on
+      // how the replicas are spread over ranks
+      std::vector<uint64_t> fx(size_t(T) * ns + size_t(T), 0);
+      for (size_t r = 0; r < Rl; r++) {
+        if (wait[r]) continue;
         for (unsigned i = 0; i < ns; i++)
           fx[(r / R) * ns + i] += uint64_t(int64_t(std::llround(sb_rep[r * ns + i] * 4294967296.0)));
+        fx[size_t(T) * ns + r / R] += 1; // participants of the transition
+      }
       ERUN(hmc_comm_allreduce_host_u64(comm, fx.data(), fx.size(), 0));
-      for (size_t k = 0; k < fx.size(); k++)
-        sb[k] = double(int64_t(fx[k])) / (4294967296.0 * double(R) * double(world));
+      for (int t = 0; t < T; t++)
+        for (unsigned i = 0; i < ns; i++)
+          sb[size_t(t) * ns + i] = double(int64_t(fx[size_t(t) * ns + i])) /
+                                   (4294967296.0 * double(std::max<uint64_t>(1, fx[size_t(T) * ns + t])));
       ERUN(hmc_set_s_bias(h, sb.data(), int(ns)));
     }
   } else if (opt->independent) {
@@ -443,7 +460,7 @@ extern "C" int hmc_run_program_ensemble(const hmc_params *tr, int T, int device,
   }
 
   // the G-test rounds, main.cc:451-491
-  std::vector<uint8_t> done_t(T, 0), skip(Rl, 0), done_r(opt->independent ? Rl : 0, 0);
+  std::vector<uint8_t> done_t(T, 0), failed_t(T, 0), skip(Rl, 0), done_r(opt->independent ? Rl : 0, 0);
   std::vector<uint32_t> rounds_r(opt->independent ? Rl : 0, 0);
   std::vector<uint64_t> cc(size_t(T) * ns), cc_rep(opt->independent ? Rl * ns : 0);
   std::vector<uint32_t> err(Rl);
@@ -479,10 +496,14 @@ extern "C" int hmc_run_program_ensemble(const hmc_params *tr, int T, int device,
         err_t[t] = e;
       }
     }
-    bool fatal = false;
+    // (per transition, like the reference's one process per transition: the others go on)
     for (int t = 0; t < T; t++) {
+      if (done_t[t]) continue;
       res[t].err_flags |= uint32_t(err_t[t]);
-      if (uint32_t(err_t[t]) & FATAL_FLAGS) fatal = true;
+      if (uint32_t(err_t[t]) & FATAL_FLAGS) {
+        failed_t[t] = 1;
+        rc_final = -8;
+      }
     }
     if (dist_cap) {
       dist_buf.resize(Rl * dist_cap * nl_max);
@@ -520,12 +541,16 @@ extern "C" int hmc_run_program_ensemble(const hmc_params *tr, int T, int device,
         sink->on_config_int(sink->user, t, vals.data(), unsigned(vals.size()));
       }
     }
-    if (fatal) {
-      rc_final = -8;
-      if (tot) std::snprintf(tot->message, sizeof tot->message,
-                             "replica error flags raised in round %u (see err_flags)", rnd);
-      break;
-    }
+    for (int t = 0; t < T; t++)
+      if (failed_t[t] && !done_t[t]) {
+        done_t[t] = 1; // stops here; res[t].accepted stays 0 and err_flags says why
+        for (unsigned j = 0; j < R; j++) skip[size_t(t) * R + j] = 1;
+        if (opt->independent)
+          for (unsigned j = 0; j < R; j++) done_r[size_t(t) * R + j] = 1;
+        if (tot) std::snprintf(tot->message, sizeof tot->message,
+                               "replica error flags raised (first in transition %d, round %u; see err_flags)",
+                               t, rnd);
+      }
     bool all_done = true;
     if (!opt->independent) {
       for (int t = 0; t < T; t++) {

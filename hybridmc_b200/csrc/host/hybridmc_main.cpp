@@ -322,6 +322,7 @@ void usage() {
                "  --eq-iters arg        equilibration iterations (default min(total_iter_eq, 8))\n"
                "  --max-rounds arg      G-test rounds at most (default max_g_test_count)\n"
                "  --no-wl               skip the Wang-Landau pre-estimate\n"
+               "  --wl-replicas arg (=0) replicas that run the Wang-Landau phase (0: all)\n"
                "  --hist-bins arg (=0)  pooled distance histograms -> dataset dist_hist\n"
                "  --nccl-id-file arg    multi-GPU: one process per GPU (RANK, WORLD_SIZE,\n"
                "                        LOCAL_RANK in the environment), the replicas of the\n"
@@ -340,6 +341,7 @@ int main(int argc, char *argv[]) {
   int device = 0;
   bool hdf5 = true;
   unsigned replicas = 0, iters_per_round = 0, eq_iters = 0, max_rounds = 0, hist_bins = 0;
+  unsigned wl_replicas = 0;
   bool no_wl = false, device_given = false;
   std::string nccl_id_file;
   try {
@@ -374,6 +376,7 @@ int main(int argc, char *argv[]) {
       else if (take("eq-iters")) eq_iters = unsigned(std::atoi(val.c_str()));
       else if (take("max-rounds")) max_rounds = unsigned(std::atoi(val.c_str()));
       else if (take("hist-bins")) hist_bins = unsigned(std::atoi(val.c_str()));
+      else if (take("wl-replicas")) wl_replicas = unsigned(std::atoi(val.c_str()));
       else if (take("nccl-id-file")) nccl_id_file = val;
       else if (a == "--no-wl") no_wl = true;
       else if (take("output-format")) {
@@ -477,6 +480,7 @@ int main(int argc, char *argv[]) {
       opt.max_rounds = max_rounds;
       opt.wang_landau = no_wl ? 0u : 1u;
       opt.hist_bins = hist_bins;
+      opt.wl_replicas = wl_replicas;
       opt.hist_rmax = p.length * 0.5 * std::sqrt(3.0); // the longest min-image distance
       opt.dist_rows = p.total_iter * p.nsteps;          // the reference's rows per round
       opt.config_int_rows = p.total_iter * p.nsteps / p.write_step + p.total_iter * p.mc_write;

@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libhybridmc_b200.so")
 
 # every symbol include/hybridmc_b200.h declares
 EXPORTS = [
-    "hmc_timer_start", "hmc_timer_stop",
+    "hmc_timer_start", "hmc_timer_stop", "hmc_resident_replicas",
     "hmc_create", "hmc_destroy", "hmc_last_error", "hmc_abi_version",
     "hmc_set_positions", "hmc_get_positions", "hmc_get_velocities", "hmc_set_config",
     "hmc_get_config", "hmc_init_config_from_positions", "hmc_set_s_bias", "hmc_get_s_bias",
@@ -417,6 +417,14 @@ def init_pos_chain(params, seeds=None):
     return pos
 
 
+def resident_replicas(nbeads, device=0):
+    """replicas of an nbeads-bead chain that run concurrently on one GPU"""
+    n = load_library().hmc_resident_replicas(C.c_uint(int(nbeads)), int(device))
+    if n < 0:
+        raise EngineError("hmc_resident_replicas: no CUDA device %d" % device)
+    return int(n)
+
+
 def fp64_peak(device=0):
     """(DFMA TFLOP/s, DMUL+DADD TFLOP/s) measured on `device`."""
     lib = load_library()
@@ -537,7 +545,8 @@ class EnsembleOptions(C.Structure):
                 ("wang_landau", C.c_uint32), ("independent", C.c_uint32),
                 ("hist_bins", C.c_uint32), ("dist_rows", C.c_uint32),
                 ("config_int_rows", C.c_uint32), ("seed0", C.c_uint32), ("seed1", C.c_uint32),
-                ("pad", C.c_uint32), ("hist_rmax", C.c_double), ("comm", C.c_void_p)]
+                ("wl_replicas", C.c_uint32), ("hist_rmax", C.c_double), ("comm", C.c_void_p),
+                ("start_s_bias", C.c_void_p)]
 
 
 class EnsembleResult(C.Structure):
@@ -578,7 +587,7 @@ class EnsembleError(EngineError):
 def run_program_ensemble(params_list, start_pos, replicas, device=0, seed=(1, 2),
                          iters_per_round=0, eq_iters=0, max_rounds=0, wl=True,
                          independent=False, hist_bins=0, hist_rmax=0.0, dist_rows=0,
-                         config_int_rows=0, comm=None, verbose=False, keep_rounds=None):
+                         config_int_rows=0, comm=None, verbose=False, keep_rounds=None, wl_replicas=0, start_s_bias=None, strict=True):
     """hmc_run_program_ensemble: the reference's per-transition program (main.cc:411-491)
     for T transitions of one layer x `replicas` replicas each on THIS rank, pooled over the
     ranks of `comm`.  Returns a dict: s_bias[T][nstates], rounds[T], accepted[T], counts[T],
@@ -601,7 +610,12 @@ def run_program_ensemble(params_list, start_pos, replicas, device=0, seed=(1, 2)
                           hist_bins=int(hist_bins), dist_rows=int(dist_rows),
                           config_int_rows=int(config_int_rows), seed0=int(seed[0]) & 0xffffffff,
                           seed1=int(seed[1]) & 0xffffffff, hist_rmax=float(hist_rmax),
+                          wl_replicas=int(wl_replicas),
                           comm=comm.c if comm is not None else None)
+    if start_s_bias is not None:
+        sb0 = np.zeros((T, 16))
+        sb0[:, :ns] = np.asarray(start_s_bias, dtype=np.float64).reshape(T, ns)
+        opt.start_s_bias = sb0.ctypes.data
     rounds_log = [[] for _ in range(T)]
     dist = [[] for _ in range(T)]
     cfg = [[] for _ in range(T)]
@@ -664,7 +678,10 @@ def run_program_ensemble(params_list, start_pos, replicas, device=0, seed=(1, 2)
                                      for h in hist])
     if independent:
         out["replicas"] = repl
-    if rc != 0:
+    # transitions stopped by a replica error flag (the reference's process would have died
+    # with an exception); the other transitions of the batch are complete
+    out["failed"] = (out["err"] & ~np.uint32(ERR_SAMPLE_OVERFLOW)) != 0
+    if rc != 0 and (strict or rc != -8):
         raise EnsembleError(tot.message.decode() or "hmc_run_program_ensemble failed (%d)" % rc,
                             results=out, code=rc)
     return out

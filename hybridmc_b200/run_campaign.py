@@ -71,8 +71,8 @@ def stair_stages(d, layer, master_rc, stair_rc):
 def layer_replicas(replicas, n_transitions, world=1, fill=0):
     """Replicas per transition on ONE rank.  `replicas` is the total per transition over all
     ranks; with fill > 0 thin layers are topped up until about `fill` replicas run per GPU
-    (a 10-transition layer would otherwise leave most of the 148 SMs idle; the rounds get
-    proportionally shorter because iterations per round = total_iter / replicas)."""
+    (a 10-transition layer would otherwise leave most of the 148 SMs idle; the extra replicas
+    cost no time and add samples)."""
     per_rank = -(-replicas // world)
     if fill and n_transitions * per_rank < fill:
         per_rank = -(-fill // n_transitions)
@@ -82,11 +82,15 @@ def layer_replicas(replicas, n_transitions, world=1, fill=0):
 def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, max_rounds=40,
                  max_layers=None, hist_bins=2048, rank=0, world=1, log=print, wl=True,
                  eq_iters=None, seed_increment=1, stair_bp=None, stair_rc=None, comm=None,
-                 fill=0, dist_rows=None, config_int_rows=None, keep_rounds=4):
+                 fill=0, dist_rows=None, config_int_rows=None, keep_rounds=4, wl_replicas=0, warm_start=False):
     """stair_bp / stair_rc: init_json.py's --bp / --rc — the transitions that form bond
     `stair_bp` run as a sequence of stages with shrinking rc, each started from the previous
     stage's structure; stage j of all of a layer's staircase transitions is one ensemble.
     `replicas`: per transition, summed over the ranks of `comm`.
+    warm_start: a transition that forms bond b on top of the bonds B starts its
+    flat-histogram iteration from the converged s_bias of "b on top of B minus one bond" of
+    the previous layer (the smallest of those values: an estimate that is too low climbs
+    faster than one that is too high descends, entropy.cc:46-63) instead of init_s.
     Returns (summary rows, seconds, collision events)."""
     from .params import params_from_json
     os.makedirs(out_dir, exist_ok=True)
@@ -98,6 +102,7 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
     stair_bp = sorted(stair_bp) if stair_bp is not None else None
     summary = []
     events = 0
+    s_est = {}  # (bits_in, bits_out) -> converged s_bias[0], for warm_start
     t_start = time.time()
     for layer, trans in layers:
         if max_layers is not None and layer >= max_layers:
@@ -124,7 +129,10 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                     continue
                 path = os.path.join(out_dir, jobs[k][stage][2] + ".h5")
                 if os.path.exists(path):
-                    up = File(path)["unique_config"]["pos"]
+                    fdone = File(path)
+                    if stage == len(jobs[k]) - 1:
+                        s_est[(trans[k][0], trans[k][1])] = float(fdone["s_bias"][0])
+                    up = fdone["unique_config"]["pos"]
                     if len(up):
                         stage_pos[k] = np.array(up[0])
                         if stage == len(jobs[k]) - 1:
@@ -136,82 +144,112 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                     todo + [-1] * (len(mine) - len(todo)), dtype=np.int64)) if k >= 0]
             if not todo:
                 continue
-            params = [jobs[k][stage][0] for k in todo]
-            p0 = params[0]
-            R = layer_replicas(replicas, len(todo), world, fill)
-            # raw rows kept per transition and round (the reference: total_iter * nsteps per
-            # round, all rounds; here bounded — the pooled dist_hist is the full statistic)
-            rows = min(p0.total_iter * p0.nsteps, 4096) if dist_rows is None else dist_rows
-            cfgs = (min(p0.total_iter * (p0.nsteps // max(p0.write_step, 1) + p0.mc_write + 1), 4096)
-                    if config_int_rows is None else config_int_rows)
-            t0 = time.time()
-            try:
+            for attempt in range(3):
+                params = [jobs[k][stage][0] for k in todo]
+                p0 = params[0]
+                R = layer_replicas(replicas, len(todo), world, fill)
+                # iterations per replica and round follow the NOMINAL replica count: topping a thin
+                # layer up adds samples, it must not shorten the trajectories (a slowly mixing
+                # transition needs every replica to run several relaxation times per round)
+                iters = iters_per_round or max(1, -(-p0.total_iter // max(replicas, 1)))
+                # raw rows kept per transition and round (the reference: total_iter * nsteps per
+                # round, all rounds; here bounded — the pooled dist_hist is the full statistic)
+                rows = min(p0.total_iter * p0.nsteps, 4096) if dist_rows is None else dist_rows
+                cfgs = (min(p0.total_iter * (p0.nsteps // max(p0.write_step, 1) + p0.mc_write + 1), 4096)
+                        if config_int_rows is None else config_int_rows)
+                start_sb = None
+                if warm_start and p0.nstates == 2:
+                    start_sb = np.zeros((len(todo), 2))
+                    for n, k in enumerate(todo):
+                        b_in, b_out = trans[k][0], trans[k][1]
+                        new = [i for i in range(nb_bonds) if b_in[i] != b_out[i]][0]
+                        guesses = []
+                        for c in range(nb_bonds):
+                            if b_in[c]:
+                                pi = tuple(x and i != c for i, x in enumerate(b_in))
+                                po = tuple(x or i == new for i, x in enumerate(pi))
+                                if (pi, po) in s_est:
+                                    guesses.append(s_est[(pi, po)])
+                        start_sb[n, 0] = min(guesses) if guesses and stage == 0 else 3.0
+                t0 = time.time()
                 out = run_transition_ensemble(
                     params, [stage_pos[k] for k in todo], R, device=device,
-                    seed=(p0.seeds[0], 1 + layer + 64 * stage), iters_per_round=iters_per_round,
+                    seed=(p0.seeds[0] + 7919 * attempt, 1 + layer + 64 * stage), iters_per_round=iters,
                     max_rounds=max_rounds, hist_bins=hist_bins, hist_rmax=rmax, wl=wl,
                     eq_iters=eq_iters, comm=comm, dist_rows=rows, config_int_rows=cfgs,
-                    keep_rounds=keep_rounds)
-            except EnsembleError as ex:
-                # the reference's process dies with an exception here (main.cc:48-56,219-225):
-                # nothing of this batch is written as valid output
-                bad = [jobs[k][stage][2] for n, k in enumerate(todo)
-                       if ex.results is not None and ex.results["err"][n] & ~np.uint32(32)]
-                log("layer %d: replica error flags in %s" % (layer, bad))
-                raise
-            dt = time.time() - t0
-            events += int(out["events"][0])
-            for n, k in enumerate(todo):
-                bits_in, bits_out, _ = trans[k]
-                p, dj, name = jobs[k][stage]
-                up = out["unique_pos"][n]
-                summary.append((fmt(bits_in), name.split("_", 3)[3], float(out["s_bias"][n][0])))
-                if up is not None:
-                    stage_pos[k] = up
+                    keep_rounds=keep_rounds, wl_replicas=wl_replicas, start_s_bias=start_sb,
+                    strict=False)
+                # a transition stopped by a replica error flag: the reference's process dies with
+                # an exception there (main.cc:48-56,219-225) and tools/rerun.py runs it again;
+                # nothing of it is written, the loop below comes back to it with another seed
+                failed = [k for n, k in enumerate(todo) if out["failed"][n]]
+                if failed:
+                    log("layer %d: replica error flags in %s (attempt %d)" % (
+                        layer, [(jobs[k][stage][2], int(out["err"][todo.index(k)])) for k in failed], attempt))
+                dt = time.time() - t0
+                events += int(out["events"][0])
+                for n, k in enumerate(todo):
+                    if out["failed"][n]:
+                        continue
+                    bits_in, bits_out, _ = trans[k]
+                    p, dj, name = jobs[k][stage]
+                    up = out["unique_pos"][n]
+                    summary.append((fmt(bits_in), name.split("_", 3)[3], float(out["s_bias"][n][0])))
                     if stage == len(jobs[k]) - 1:
-                        new_structs.setdefault(bits_out, up)
-                elif stage < len(jobs[k]) - 1:
-                    raise RuntimeError("%s: no bonded structure to start the next stair stage from" % name)
-                if rank != 0:
-                    continue
-                with open(os.path.join(out_dir, name + ".json"), "w") as f:
-                    json.dump(dj, f)
-                uv = out["unique_vel"][n]
-                cr = out["counts_rounds"][n]
-                nl = max(p.n_nonlocal, 1)
-                ds = {"s_bias": out["s_bias"][n].astype(np.float32),  # f32 as main.cc:445-446
-                      # ConfigCountWriter: a zero row, then one row per G-test round
-                      # (main.cc:394,488)
-                      "config_count": np.vstack([np.zeros((1, p.nstates), np.uint64),
-                                                 cr if len(cr) else out["counts"][n][None]]),
-                      # per-MD-step bond distances of the last rounds (main.cc:199-200); what
-                      # tools/mfpt.py:76-77 reads
-                      "dist": out["dist"][n].reshape(-1, nl),
-                      "config/int": out["config_int"][n],
-                      "dist_hist": out["dist_hist"][n],
-                      "unique_config/pos": (up[None] if up is not None
-                                            else np.zeros((0, p.nbeads, 3))),
-                      "unique_config/vel": (uv[None] if uv is not None
-                                            else np.zeros((0, p.nbeads, 3))),
-                      "unique_config/config": np.ones(1 if up is not None else 0, np.uint64)}
-                at = {"sigma": np.float64(p.sigma), "length": np.float64(p.length),
-                      "nsteps": np.uint32(p.nsteps), "dist_hist_rmax": np.float64(rmax),
-                      "replicas": np.uint32(R * world), "err_flags": np.uint32(out["err"][n]),
-                      "nonlocal_bonds": np.array(p.bond_list("nonlocal"), np.uint32).reshape(-1, 2),
-                      "transient_bonds": np.array(p.bond_list("transient"), np.uint32).reshape(-1, 2),
-                      "permanent_bonds": np.array(p.bond_list("permanent"), np.uint32).reshape(-1, 2)}
-                write_output(os.path.join(out_dir, name + ".h5"), ds, at)
-                with open(os.path.join(out_dir, name + ".log"), "w") as f:
-                    f.write("replicas %d rounds %d accepted %s s_bias %s counts %s err_flags %d\n" % (
-                        R * world, out["rounds"][n], bool(out["accepted"][n]),
-                        out["s_bias"][n].tolist(), out["counts"][n].tolist(), int(out["err"][n])))
-            if rank == 0:
-                log("layer %d%s: %d transitions, %d replicas each%s, rounds %s, %.1f s (%.1f s device), "
-                    "events %d, collectives %d" % (
-                        layer, " stage %d" % stage if stage else "", len(todo), R * world,
-                        " over %d ranks" % world if world > 1 else "",
-                        _brief(out["rounds"]), dt, out["seconds_device"], int(out["events"][0]),
-                        out["collectives"]))
+                        s_est[(bits_in, bits_out)] = float(out["s_bias"][n][0])
+                    if up is not None:
+                        stage_pos[k] = up
+                        if stage == len(jobs[k]) - 1:
+                            new_structs.setdefault(bits_out, up)
+                    elif stage < len(jobs[k]) - 1:
+                        raise RuntimeError("%s: no bonded structure to start the next stair stage from" % name)
+                    if rank != 0:
+                        continue
+                    with open(os.path.join(out_dir, name + ".json"), "w") as f:
+                        json.dump(dj, f)
+                    uv = out["unique_vel"][n]
+                    cr = out["counts_rounds"][n]
+                    nl = max(p.n_nonlocal, 1)
+                    ds = {"s_bias": out["s_bias"][n].astype(np.float32),  # f32 as main.cc:445-446
+                          # ConfigCountWriter: a zero row, then one row per G-test round
+                          # (main.cc:394,488)
+                          "config_count": np.vstack([np.zeros((1, p.nstates), np.uint64),
+                                                     cr if len(cr) else out["counts"][n][None]]),
+                          # per-MD-step bond distances of the last rounds (main.cc:199-200); what
+                          # tools/mfpt.py:76-77 reads
+                          "dist": out["dist"][n].reshape(-1, nl) if "dist" in out else np.zeros((0, nl)),
+                          "config/int": (out["config_int"][n] if "config_int" in out
+                                         else np.zeros(0, np.uint64)),
+                          "dist_hist": out["dist_hist"][n],
+                          "unique_config/pos": (up[None] if up is not None
+                                                else np.zeros((0, p.nbeads, 3))),
+                          "unique_config/vel": (uv[None] if uv is not None
+                                                else np.zeros((0, p.nbeads, 3))),
+                          "unique_config/config": np.ones(1 if up is not None else 0, np.uint64)}
+                    at = {"sigma": np.float64(p.sigma), "length": np.float64(p.length),
+                          "nsteps": np.uint32(p.nsteps), "dist_hist_rmax": np.float64(rmax),
+                          "replicas": np.uint32(R * world), "err_flags": np.uint32(out["err"][n]),
+                          "nonlocal_bonds": np.array(p.bond_list("nonlocal"), np.uint32).reshape(-1, 2),
+                          "transient_bonds": np.array(p.bond_list("transient"), np.uint32).reshape(-1, 2),
+                          "permanent_bonds": np.array(p.bond_list("permanent"), np.uint32).reshape(-1, 2)}
+                    write_output(os.path.join(out_dir, name + ".h5"), ds, at)
+                    with open(os.path.join(out_dir, name + ".log"), "w") as f:
+                        f.write("replicas %d rounds %d accepted %s s_bias %s counts %s err_flags %d\n" % (
+                            R * world, out["rounds"][n], bool(out["accepted"][n]),
+                            out["s_bias"][n].tolist(), out["counts"][n].tolist(), int(out["err"][n])))
+                if rank == 0:
+                    log("layer %d%s: %d transitions, %d replicas each%s, rounds %s, %.1f s (%.1f s device), "
+                        "events %d, collectives %d" % (
+                            layer, " stage %d" % stage if stage else "", len(todo), R * world,
+                            " over %d ranks" % world if world > 1 else "",
+                            _brief(out["rounds"]), dt, out["seconds_device"], int(out["events"][0]),
+                            out["collectives"]))
+                todo = failed
+                if not todo:
+                    break
+            if todo:
+                raise RuntimeError("layer %d: %d transitions still raise replica error flags after 3 "
+                                   "attempts: %s" % (layer, len(todo), [jobs[k][stage][2] for k in todo]))
         for b_, v in new_structs.items():
             structures.setdefault(b_, v)
         missing = [t[1] for lt in layers[layer + 1:layer + 2] for t in lt[1] if t[0] not in structures]
@@ -241,8 +279,12 @@ def main(argv=None):
     ap.add_argument("--out", default=None, help="output directory (default: <json name>)")
     ap.add_argument("--replicas", type=int, default=512,
                     help="replicas per transition (in total over all ranks)")
-    ap.add_argument("--fill", type=int, default=0,
-                    help="top thin layers up to about this many replicas per GPU")
+    ap.add_argument("--fill", default="0",
+                    help="top thin layers up to about this many replicas per GPU "
+                         "('auto': what the GPU runs concurrently)")
+    ap.add_argument("--total-iter", type=int, default=None,
+                    help="override total_iter of the master json (iterations a G-test round "
+                         "pools over all replicas of a transition)")
     ap.add_argument("--device", type=int, default=None)
     ap.add_argument("--iters-per-round", type=int, default=None)
     ap.add_argument("--max-rounds", type=int, default=40)
@@ -250,11 +292,20 @@ def main(argv=None):
     ap.add_argument("--no-wl", action="store_true", help="skip the per-replica Wang-Landau pre-estimate")
     ap.add_argument("--eq-iters", type=int, default=None)
     ap.add_argument("--hist-bins", type=int, default=2048)
+    ap.add_argument("--warm-start", action="store_true",
+                    help="start s_bias from the same bond's converged value one layer earlier")
+    ap.add_argument("--wl-replicas", type=int, default=0,
+                    help="replicas per transition that run the Wang-Landau phase (0: all)")
+    ap.add_argument("--dist-rows", type=int, default=None,
+                    help="raw dist rows kept per transition and round (default min(total_iter*nsteps, 4096))")
+    ap.add_argument("--config-int-rows", type=int, default=None)
     args = ap.parse_args(argv)
     if bool(args.rc) != bool(args.bp):
         ap.error("--rc and --bp go together (tools/init_json.py:180-183)")
     with open(args.json) as f:
         master = json.load(f)
+    if args.total_iter:
+        master["total_iter"] = args.total_iter
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     device = args.device if args.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
@@ -266,11 +317,14 @@ def main(argv=None):
     # invoked the way tools/run.py invokes init_json.py: outputs go to the current directory
     out_dir = args.out or ("." if args.exe is not None else
                            os.path.splitext(os.path.basename(args.json))[0])
+    from .engine import resident_replicas
+    fill = resident_replicas(master["nbeads"], device) if args.fill == "auto" else int(args.fill)
     summary, wall, events = run_campaign(
         master, out_dir, args.replicas, device, args.iters_per_round, args.max_rounds,
         args.max_layers, hist_bins=args.hist_bins, rank=rank, world=world, wl=not args.no_wl,
         eq_iters=args.eq_iters, seed_increment=args.seed_increment, stair_bp=args.bp,
-        stair_rc=args.rc, comm=comm, fill=args.fill)
+        stair_rc=args.rc, comm=comm, fill=fill, dist_rows=args.dist_rows,
+        config_int_rows=args.config_int_rows, wl_replicas=args.wl_replicas, warm_start=args.warm_start)
     if rank == 0:
         print("%d transitions on %d GPU(s) in %.1f s -> %.0f transitions/hour, %.3e collision "
               "events (%.3e events/s whole campaign)" % (

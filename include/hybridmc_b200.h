@@ -457,9 +457,18 @@ typedef struct hmc_ensemble_options {
                                (replica-major subsample) for the `dist` dataset */
   uint32_t config_int_rows; /* >0: likewise config/int entries */
   uint32_t seed0, seed1;    /* Philox key */
-  uint32_t pad;
+  uint32_t wl_replicas;     /* wang_landau = 1: how many replicas of a transition (over all
+                               ranks, spread evenly: global id % stride == 0) run the
+                               Wang-Landau phase; the others wait.  0: all of them.  The
+                               phase is 1/gamma_f sequential steps per replica whatever the
+                               ensemble size, so in a layer of many transitions a few
+                               replicas per transition give the start value at a fraction
+                               of the device time */
   double hist_rmax;
   hmc_comm comm;            /* NULL: one rank */
+  const double *start_s_bias; /* NULL: init_s (entropy.cc:14-20); else [T][16] start values
+                               of the flat-histogram iteration, e.g. the converged value of
+                               the same bond one lattice layer earlier (fewer rounds) */
 } hmc_ensemble_options;
 
 typedef struct hmc_ensemble_result { /* one per transition */
@@ -513,6 +522,10 @@ int hmc_run_program_ensemble(const hmc_params *transitions, int n_transitions, i
 /* kernels launched by this handle so far, and the device time (ms, CUDA
  * events on the handle's stream) of the last hmc_run / injected call. */
 int hmc_get_launch_stats(hmc_handle h, uint64_t *n_launches, float *last_ms);
+/* Replicas of an nbeads-bead chain that run concurrently on `device` (SMs x resident warps
+ * x replicas per warp): ensembles smaller than this leave SMs idle, so a campaign tops thin
+ * lattice layers up to it.  <0: no such device. */
+int hmc_resident_replicas(unsigned nbeads, int device);
 /* Interval timer on the handle's stream (CUDA events): everything enqueued between the two
  * calls — kernels, the NCCL all-reduce of hmc_allreduce_counts, copies — and the host gaps
  * between them.  hmc_timer_stop synchronises and returns the milliseconds. */

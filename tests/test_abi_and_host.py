@@ -45,6 +45,26 @@ def test_params_struct_layout_matches_c():
     assert int(out) == C.sizeof(HmcParams)
 
 
+def test_ensemble_struct_layouts_match_c():
+    """the ctypes mirrors of the ensemble-program structs (engine.py) against the header"""
+    import subprocess
+    import tempfile
+    names = ["hmc_ensemble_options", "hmc_ensemble_result", "hmc_ensemble_totals", "hmc_ensemble_sink"]
+    src = ('#include "hybridmc_b200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu", '
+           + ", ".join("sizeof(%s)" % n for n in names)
+           + ', offsetof(hmc_ensemble_options, comm), offsetof(hmc_ensemble_result, unique_pos));}')
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o",
+                        os.path.join(d, "s")], check=True)
+        out = [int(x) for x in subprocess.run([os.path.join(d, "s")], capture_output=True,
+                                              text=True).stdout.split()]
+    assert out[:4] == [C.sizeof(eng.EnsembleOptions), C.sizeof(eng.EnsembleResult),
+                       C.sizeof(eng.EnsembleTotals), C.sizeof(eng.EnsembleSink)]
+    assert out[4] == eng.EnsembleOptions.comm.offset
+    assert out[5] == eng.EnsembleResult.unique_pos.offset
+
+
 def test_create_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():

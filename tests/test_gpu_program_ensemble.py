@@ -218,6 +218,23 @@ def test_error_flags_end_the_program():
     assert ei.value.results["rounds"][0] <= 1
 
 
+def test_a_failed_transition_does_not_stop_the_batch():
+    """per-transition fatality, like the reference's one process per transition: the
+    transition with the bad start structure is reported failed, its neighbour in the same
+    ensemble launch converges as if it ran alone"""
+    p = params_from_json(load_config("8bead_1bond"))
+    good = init_pos_chain(p)
+    bad = good.copy()
+    bad[3] += 0.4
+    kw = dict(seed=(7, 8), iters_per_round=4, eq_iters=4, max_rounds=30)
+    out = run_program_ensemble([p, p], [bad, good], 128, strict=False, **kw)
+    assert out["failed"].tolist() == [True, False] and out["err"][0] & 1 and out["err"][1] == 0
+    assert out["accepted"].tolist() == [False, True]
+    assert abs(out["s_bias"][1][0] - 3.6) < 0.4
+    with pytest.raises(EnsembleError):
+        run_program_ensemble([p, p], [bad, good], 128, **kw)
+
+
 def _exe():
     from hybridmc_b200.build import build_executable
     return build_executable()
