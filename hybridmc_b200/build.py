@@ -60,6 +60,26 @@ def build_library(force=False, verbose=False, out=None, defines=()):
     return out or LIB
 
 
+# Checking builds of the same sources, loaded through HMC_LIB by tests/test_gpu_debug_builds.py:
+#   verify: every pair the single-precision pre-filter drops is predicted exactly anyway and
+#           error bit 0x40000000 is raised if one of them has an event
+#   bounds: every index into the shared-memory replica image is range-checked
+VARIANTS = {"verify": ("HMC_VERIFY_PREFILTER", os.path.join(HERE, "libhybridmc_b200_verify.so")),
+            "bounds": ("HMC_DEBUG_BOUNDS", os.path.join(HERE, "libhybridmc_b200_bounds.so"))}
+
+
+def build_variants(force=False):
+    """Both checking builds, compiled concurrently."""
+    from concurrent.futures import ThreadPoolExecutor
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    todo = [(d, out) for d, out in VARIANTS.values()
+            if force or not os.path.exists(out)
+            or any(os.path.getmtime(x) > os.path.getmtime(out) for x in deps)]
+    with ThreadPoolExecutor(max_workers=2) as ex:
+        list(ex.map(lambda t: build_library(force=True, out=t[1], defines=(t[0],)), todo))
+    return {k: v[1] for k, v in VARIANTS.items()}
+
+
 EXE = os.path.join(HERE, "hybridmc")
 
 
@@ -87,3 +107,5 @@ if __name__ == "__main__":
                         out=outs[0] if outs else None, defines=defs))
     if not outs:
         print(build_executable(force="--force" in sys.argv))
+    if "--variants" in sys.argv:
+        print(build_variants(force="--force" in sys.argv))

@@ -47,6 +47,7 @@ struct hmc_engine {
   uint8_t *d_skip = nullptr;
   bool skip_on = false;
   uint32_t rng_first = 0, rng_total = 0;
+  int list_cap_override = 0; // hmc_set_list_capacity
   double *d_dist = nullptr;
   uint32_t *d_dist_n = nullptr;
   uint32_t dist_cap = 0;
@@ -121,7 +122,7 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.nb = h->nb;
   a.ncell = int(p.ncell);
   a.npairs = h->npairs;
-  a.list_cap = hmc_list_capacity(h->nb, h->group);
+  a.list_cap = hmc_list_capacity(h->nb, h->group, h->list_cap_override);
   a.nstates = h->nstates;
   a.l = p.length;
   a.inv_l = 1.0 / p.length;       // Box, box.h:15
@@ -205,7 +206,8 @@ void fill_kargs(hmc_handle h, KArgs &a) {
   a.md_draw_base = h->md_draws;
   a.mc_draw_base = h->mc_draws;
   a.work_counter = h->d_work;
-  hmc_smem_layout(h->nb, h->group, &a.off_tnn, &a.off_list, &a.off_plist, &a.smem_per_replica);
+  hmc_smem_layout(h->nb, h->group, h->list_cap_override, &a.off_tnn, &a.off_list, &a.off_plist,
+                  &a.smem_per_replica);
   a.short_chain = (double(h->nb - 1) * p.near_max < 1.45 * p.length) ? 1 : 0;
   a.chain_max = double(h->nb - 1) * p.near_max;
   {
@@ -777,6 +779,16 @@ int hmc_set_replica_ids(hmc_handle h, unsigned first, unsigned total_per_transit
   return 0;
 }
 
+int hmc_set_list_capacity(hmc_handle h, unsigned entries) {
+  if (!h) return fail(h, "null handle");
+  h->list_cap_override = int(entries);
+  return 0;
+}
+
+unsigned hmc_get_list_capacity(hmc_handle h) {
+  return h ? unsigned(hmc_list_capacity(h->nb, h->group, h->list_cap_override)) : 0u;
+}
+
 int hmc_enable_replica_counts(hmc_handle h, int on) {
   if (!h) return fail(h, "null handle");
   CK(cudaSetDevice(h->device));
@@ -1087,6 +1099,11 @@ int hmc_resident_replicas(unsigned nbeads, int device) {
   }
   // 16 warps per SM (the kernel's register budget), 32 / G replicas per warp
   return sms * 16 * (32 / hmc_pick_group(int(nbeads)));
+}
+
+long long hmc_debug_bounds_violations(void) {
+  cudaDeviceSynchronize();
+  return hmc_bounds_violations_device();
 }
 
 int hmc_timer_start(hmc_handle h) {

@@ -114,10 +114,11 @@ struct KArgs {
 cudaError_t hmc_launch(const KArgs &a, int group, cudaStream_t stream, int *grid_out,
                        int *block_out);
 size_t hmc_smem_per_replica(int nb, int group);
-int hmc_list_capacity(int nb, int group);
-void hmc_smem_layout(int nb, int group, uint32_t *off_tnn, uint32_t *off_list, uint32_t *off_plist,
+int hmc_list_capacity(int nb, int group, int override_entries);
+void hmc_smem_layout(int nb, int group, int cap_override, uint32_t *off_tnn, uint32_t *off_list, uint32_t *off_plist,
                      uint32_t *total);
 int hmc_pick_group(int nb);
+long long hmc_bounds_violations_device();
 
 // message returned by hmc_last_error(NULL) (handle-less entry points)
 void hmc_set_global_error(const char *msg);

@@ -74,6 +74,24 @@
 #define HMC_PF_UNROLL_PRAGMA
 #endif
 
+// -DHMC_DEBUG_BOUNDS: every index into the shared-memory replica image (bead records, the
+// event list, the partner list) is checked; a violation is counted (hmc_debug_bounds_violations)
+// and redirected to element 0.  The substitute for compute-sanitizer where that is not
+// available; tests/test_gpu_debug_builds.py runs the shipped configurations under it.
+#ifdef HMC_DEBUG_BOUNDS
+__device__ unsigned long long g_bounds_violations = 0ull;
+__device__ __forceinline__ int hmc_bchk(int i, int n) {
+  if (unsigned(i) >= unsigned(n)) {
+    atomicAdd(&g_bounds_violations, 1ull);
+    return 0;
+  }
+  return i;
+}
+#define HMC_IDX(i, n) hmc_bchk(int(i), int(n))
+#else
+#define HMC_IDX(i, n) (i)
+#endif
+
 namespace {
 
 // ----------------------------------------------------------------- helpers --
@@ -105,6 +123,9 @@ struct Smem {
   uint4 *le;   // [list_cap]
   uint8_t *plist; // [2 nb] + scratch: partners that survive the single-precision pre-filter
   int nb;
+#ifdef HMC_DEBUG_BOUNDS
+  int cap; // list capacity, for the index checks
+#endif
 };
 
 __device__ __forceinline__ Smem carve(unsigned char *base, const KArgs &a) {
@@ -114,6 +135,9 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const KArgs &a) {
   s.le = reinterpret_cast<uint4 *>(base + a.off_list);
   s.plist = base + a.off_plist;
   s.nb = a.nb;
+#ifdef HMC_DEBUG_BOUNDS
+  s.cap = a.list_cap;
+#endif
   return s;
 }
 
@@ -124,19 +148,19 @@ __device__ __forceinline__ double le_time(const uint4 &v) {
   return __hiloint2double(int(v.y), int(v.x));
 }
 
-#define BX(s, k) ((s).b[BSTRIDE * (k) + F_X])
-#define BY(s, k) ((s).b[BSTRIDE * (k) + F_Y])
-#define BZ(s, k) ((s).b[BSTRIDE * (k) + F_Z])
-#define BVX(s, k) ((s).b[BSTRIDE * (k) + F_VX])
-#define BVY(s, k) ((s).b[BSTRIDE * (k) + F_VY])
-#define BVZ(s, k) ((s).b[BSTRIDE * (k) + F_VZ])
-#define BT(s, k) ((s).b[BSTRIDE * (k) + F_T])
+#define BX(s, k) ((s).b[BSTRIDE * HMC_IDX(k, (s).nb) + F_X])
+#define BY(s, k) ((s).b[BSTRIDE * HMC_IDX(k, (s).nb) + F_Y])
+#define BZ(s, k) ((s).b[BSTRIDE * HMC_IDX(k, (s).nb) + F_Z])
+#define BVX(s, k) ((s).b[BSTRIDE * HMC_IDX(k, (s).nb) + F_VX])
+#define BVY(s, k) ((s).b[BSTRIDE * HMC_IDX(k, (s).nb) + F_VY])
+#define BVZ(s, k) ((s).b[BSTRIDE * HMC_IDX(k, (s).nb) + F_VZ])
+#define BT(s, k) ((s).b[BSTRIDE * HMC_IDX(k, (s).nb) + F_T])
 // packed cell index x | y << 8 | z << 16, and in the top byte the wall latched with the
 // bead's cell-crossing time
-#define BCELL(s, k) (reinterpret_cast<unsigned *>((s).b + BSTRIDE * (k) + F_CELL)[0])
-#define BWALLB(s, k) (reinterpret_cast<uint8_t *>((s).b + BSTRIDE * (k) + F_CELL)[3])
+#define BCELL(s, k) (reinterpret_cast<unsigned *>((s).b + BSTRIDE * HMC_IDX(k, (s).nb) + F_CELL)[0])
+#define BWALLB(s, k) (reinterpret_cast<uint8_t *>((s).b + BSTRIDE * HMC_IDX(k, (s).nb) + F_CELL)[3])
 // one-hot image of the cell, 10 bits per axis (ncell <= 10): 1 << x | 1 << (10 + y) | 1 << (20 + z)
-#define BOWN(s, k) (reinterpret_cast<unsigned *>((s).b + BSTRIDE * (k) + F_CELL)[1])
+#define BOWN(s, k) (reinterpret_cast<unsigned *>((s).b + BSTRIDE * HMC_IDX(k, (s).nb) + F_CELL)[1])
 
 __device__ __forceinline__ unsigned own_mask(unsigned cx, unsigned cy, unsigned cz) {
   return (1u << cx) | (1u << (10u + cy)) | (1u << (20u + cz));
@@ -625,15 +649,15 @@ __device__ __noinline__ StepOut list_merge(const KArgs &a, const Smem &s_in, int
     const int nmax = warp_max<G>(nl);
     for (int base = 0; base < nmax; base += G) {
       const int e = base + lane;
-      const uint4 v = s.le[e];
+      const uint4 v = s.le[HMC_IDX(e, a.list_cap + 32)]; // (whole lane strides: reads past nl)
       const bool m = act && e < nl && ((v.z ^ ck) & 0xffffff00u) == 0u;
-      if (m && ct < le_time(v)) s.le[e] = le_make(ct, ck);
+      if (m && ct < le_time(v)) s.le[HMC_IDX(e, a.list_cap)] = le_make(ct, ck);
       found |= m;
     }
     const unsigned fb = gl.ballot(found);
     if (act && fb == 0u) {
       if (nl < a.list_cap) {
-        if (lane == 0) s.le[nl] = le_make(ct, ck);
+        if (lane == 0) s.le[HMC_IDX(nl, a.list_cap)] = le_make(ct, ck);
         nl++;
       } else {
         err |= HMC_ERR_LIST_OVERFLOW;
@@ -670,7 +694,7 @@ __device__ __forceinline__ void commit_prediction(const KArgs &a, Rep &R, const 
   const unsigned gb = gl.ballot(app);
   const int dst = R.nl + __popc(gb & gl.below);
   const int nnew = R.nl + __popc(gb);
-  if (app && dst < a.list_cap) s.le[dst] = le_make(tt, key);
+  if (app && dst < a.list_cap) s.le[HMC_IDX(dst, a.list_cap)] = le_make(tt, key);
   if (nnew > a.list_cap) R.err |= HMC_ERR_LIST_OVERFLOW;
   R.nl = min(nnew, a.list_cap);
   const bool mrg = nl && is_cell;
@@ -831,7 +855,7 @@ __device__ HMC_COLD StepOut init_step(const KArgs &a, const Rep &R_in, const Sme
     BWALLB(s, k) = uint8_t(wall);
     // the last beads have no (k,k+1) / (k,k+2) partner
     if (k >= nb - 1) s.b[BSTRIDE * k + F_TN] = CUDART_INF;
-    if (k >= nb - 2) s.tnn[k] = CUDART_INF;
+    if (k >= nb - 2) s.tnn[HMC_IDX(k, nb)] = CUDART_INF;
   }
   __syncwarp();
   // init_nearest/nnearest_bond_events (:885-937) and add_events_for_all_beads (:540-555)
@@ -881,7 +905,7 @@ __device__ __forceinline__ void next_event(const Smem &s, Rep &R, bool coll, int
   for (int base = 0; base < nb; base += G) {
     const int k = min(base + lane, nb - 1);
     const double2 d = *reinterpret_cast<const double2 *>(s.b + BSTRIDE * k + F_TC);
-    const double t2 = s.tnn[k];
+    const double t2 = s.tnn[HMC_IDX(k, s.nb)];
     const unsigned kb = unsigned(k) * 0x00010100u; // k << 16 | k << 8
     const bool l0 = d.x < ct;
     ct = l0 ? d.x : ct;
@@ -900,13 +924,13 @@ __device__ __forceinline__ void next_event(const Smem &s, Rep &R, bool coll, int
   int nk = 0;
   for (int base = 0; base < nmax; base += G) {
     const int e = base + lane;
-    const uint4 v = s.le[e];
+    const uint4 v = s.le[HMC_IDX(e, s.cap + 32)];
     const unsigned x = v.z & 0x00ffff00u; // lo, hi
     const bool touch = ((__vcmpeq4(x, pi) | __vcmpeq4(x, pj)) & 0x00ffff00u) != 0u;
     const bool keep = e < nl && !(coll && e < n_old && touch);
     const unsigned gb = gl.ballot(keep);
     const int dst = nk + __popc(gb & gl.below); // dst <= e: never ahead of the reads
-    sts_pred_v4(s.le + dst, v, keep && coll);    // (without a collision nothing moves)
+    sts_pred_v4(s.le + HMC_IDX(dst, s.cap + 32), v, keep && coll);    // (without a collision nothing moves)
     nk += __popc(gb);
     const double t = le_time(v);
     const bool lt = keep && ((t < pt) | ((t == pt) & (v.z < pk)));
@@ -1263,9 +1287,9 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
             // (branch-free: a store that is not wanted goes to the scratch slot)
             const int dst = keep ? cnt + __popc(gbits & gl.below) : 2 * nb;
 #ifdef HMC_VERIFY_PREFILTER
-            s.plist[dst] = uint8_t((k + q * nb) | (flagged ? 0x80 : 0));
+            s.plist[HMC_IDX(dst, 2 * nb + 1)] = uint8_t((k + q * nb) | (flagged ? 0x80 : 0));
 #else
-            s.plist[dst] = uint8_t(k + q * nb);
+            s.plist[HMC_IDX(dst, 2 * nb + 1)] = uint8_t(k + q * nb);
 #endif
             cnt += __popc(gbits);
           }
@@ -1277,10 +1301,10 @@ __device__ __forceinline__ void event_body(const KArgs &a, Rep &R, const Smem &s
           const int e = base + lane;
           const bool on = e < cnt;
 #ifdef HMC_VERIFY_PREFILTER
-          const int raw = on ? int(s.plist[e]) : 0;
+          const int raw = on ? int(s.plist[HMC_IDX(e, 2 * nb + 1)]) : 0;
           const int idx = raw & 0x7f;
 #else
-          const int idx = on ? int(s.plist[e]) : 0;
+          const int idx = on ? int(s.plist[HMC_IDX(e, 2 * nb + 1)]) : 0;
 #endif
           const bool second = idx >= nb;
           const int b = second ? bj : bi;
@@ -1853,7 +1877,7 @@ int hmc_pick_group(int nb);
 // bytes of a replica image besides the event list
 static size_t smem_fixed(int nb) { return 8 * size_t(BSTRIDE) * nb + 8 * size_t(nb) + 2 * size_t(nb) + 1 + 32; }
 
-int hmc_list_capacity(int nb, int group) {
+int hmc_list_capacity(int nb, int group, int override_entries) {
   // Live nonlocal predictions per replica: ~0.5 nb on average; the list transiently also
   // holds the predictions of the running event.  Peaks measured on the CPU (2e5-event
   // probes): 1.5 nb for 46-50 beads, 2.4 nb for 20 beads with permanent bonds, with a slowly
@@ -1864,9 +1888,10 @@ int hmc_list_capacity(int nb, int group) {
   int want = (7 * nb + 1) / 2;
   if (want < 96) want = 96;
   int cap = want;
-  if (const char *e = getenv("HMC_LIST_CAP")) { // tuning / test knob
-    const int v = atoi(e);
-    if (v > 0) cap = want = v;
+  const char *e = getenv("HMC_LIST_CAP"); // tuning / test knob
+  const int forced = override_entries > 0 ? override_entries : (e ? atoi(e) : 0);
+  if (forced > 0) { // hmc_set_list_capacity: compact states (many bonds formed) need more
+    cap = want = forced;
   } else {
     const long long replicas = 16ll * (32 / group);               // per SM at 16 warps
     const long long budget = (233472ll - 4 * (1024 + 512)) / replicas; // bytes per replica
@@ -1881,9 +1906,9 @@ int hmc_list_capacity(int nb, int group) {
 }
 
 // byte offsets of the arrays inside a replica image (see Smem)
-void hmc_smem_layout(int nb, int group, uint32_t *off_tnn, uint32_t *off_list, uint32_t *off_plist,
-                     uint32_t *total) {
-  const size_t cap = size_t(hmc_list_capacity(nb, group));
+void hmc_smem_layout(int nb, int group, int cap_override, uint32_t *off_tnn, uint32_t *off_list,
+                     uint32_t *off_plist, uint32_t *total) {
+  const size_t cap = size_t(hmc_list_capacity(nb, group, cap_override));
   const size_t tnn = 8 * size_t(BSTRIDE) * nb;   // bead records are 80 B: 16-byte aligned
   size_t list = tnn + 8 * size_t(nb);
   list = (list + 15) & ~size_t(15);               // 16-byte entries
@@ -1897,7 +1922,7 @@ void hmc_smem_layout(int nb, int group, uint32_t *off_tnn, uint32_t *off_list, u
 
 size_t hmc_smem_per_replica(int nb, int group) {
   uint32_t total = 0;
-  hmc_smem_layout(nb, group, nullptr, nullptr, nullptr, &total);
+  hmc_smem_layout(nb, group, 0, nullptr, nullptr, nullptr, &total);
   return total;
 }
 
@@ -1981,4 +2006,15 @@ cudaError_t hmc_launch(const KArgs &a, int group, cudaStream_t stream, int *grid
   // SC: min-image fast path for chains shorter than 1.5 boxes, chosen per launch
   return a.short_chain ? launch_sc<true>(a, group, stream, grid_out, block_out)
                        : launch_sc<false>(a, group, stream, grid_out, block_out);
+}
+
+// violations counted by a -DHMC_DEBUG_BOUNDS build so far; -1: not such a build
+long long hmc_bounds_violations_device() {
+#ifdef HMC_DEBUG_BOUNDS
+  unsigned long long v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_bounds_violations, sizeof v) != cudaSuccess) return -2;
+  return (long long)v;
+#else
+  return -1;
+#endif
 }

@@ -365,6 +365,7 @@ extern "C" int hmc_run_program_ensemble(const hmc_params *tr, int T, int device,
   }
   const EnsembleFail efail{h, tot};
   ERUN(hmc_set_replica_ids(h, rank * R, R * world));
+  if (opt->list_capacity) ERUN(hmc_set_list_capacity(h, opt->list_capacity));
   {
     std::vector<double> pos(Rl * nb * 3);
     for (int t = 0; t < T; t++)

@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libhybridmc_b200.so")
 
 # every symbol include/hybridmc_b200.h declares
 EXPORTS = [
-    "hmc_timer_start", "hmc_timer_stop", "hmc_resident_replicas",
+    "hmc_timer_start", "hmc_timer_stop", "hmc_resident_replicas", "hmc_debug_bounds_violations",
     "hmc_create", "hmc_destroy", "hmc_last_error", "hmc_abi_version",
     "hmc_set_positions", "hmc_get_positions", "hmc_get_velocities", "hmc_set_config",
     "hmc_get_config", "hmc_init_config_from_positions", "hmc_set_s_bias", "hmc_get_s_bias",
@@ -45,7 +45,8 @@ EXPORTS = [
     "hmc_allreduce_counts", "hmc_allreduce_totals", "hmc_allreduce_hist",
     "hmc_comm_allreduce_host_u64", "hmc_comm_bcast_host", "hmc_comm_allreduce_device_u64",
     "hmc_set_replica_ids", "hmc_enable_replica_counts", "hmc_get_replica_counts",
-    "hmc_set_replica_skip", "hmc_run_program_ensemble",
+    "hmc_set_replica_skip", "hmc_run_program_ensemble", "hmc_set_list_capacity",
+    "hmc_get_list_capacity",
     "hmc_h5_create", "hmc_h5_dataset", "hmc_h5_attribute", "hmc_h5_write", "hmc_h5_destroy",
 ]
 
@@ -84,6 +85,7 @@ def load_library(path=None):
     lib.hmc_g_test.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                C.c_void_p]
     lib.hmc_enable_dist_hist.argtypes = [C.c_void_p, C.c_uint, C.c_double]
+    lib.hmc_debug_bounds_violations.restype = C.c_longlong
     lib.hmc_comm_collectives.restype = C.c_uint64
     lib.hmc_comm_collectives.argtypes = [C.c_void_p]
     lib.hmc_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
@@ -154,6 +156,13 @@ class Engine:
 
     def allreduce_hist(self, comm):
         self._ck(self.lib.hmc_allreduce_hist(self.h, comm.c if comm is not None else None))
+
+    def set_list_capacity(self, entries):
+        """entries of the per-replica list of live nonlocal predictions (0: default)"""
+        self._ck(self.lib.hmc_set_list_capacity(self.h, C.c_uint(int(entries))))
+
+    def get_list_capacity(self):
+        return int(self.lib.hmc_get_list_capacity(self.h))
 
     def enable_replica_counts(self, on=True):
         self._ck(self.lib.hmc_enable_replica_counts(self.h, 1 if on else 0))
@@ -546,7 +555,7 @@ class EnsembleOptions(C.Structure):
                 ("hist_bins", C.c_uint32), ("dist_rows", C.c_uint32),
                 ("config_int_rows", C.c_uint32), ("seed0", C.c_uint32), ("seed1", C.c_uint32),
                 ("wl_replicas", C.c_uint32), ("hist_rmax", C.c_double), ("comm", C.c_void_p),
-                ("start_s_bias", C.c_void_p)]
+                ("list_capacity", C.c_uint32), ("pad2", C.c_uint32), ("start_s_bias", C.c_void_p)]
 
 
 class EnsembleResult(C.Structure):
@@ -587,7 +596,8 @@ class EnsembleError(EngineError):
 def run_program_ensemble(params_list, start_pos, replicas, device=0, seed=(1, 2),
                          iters_per_round=0, eq_iters=0, max_rounds=0, wl=True,
                          independent=False, hist_bins=0, hist_rmax=0.0, dist_rows=0,
-                         config_int_rows=0, comm=None, verbose=False, keep_rounds=None, wl_replicas=0, start_s_bias=None, strict=True):
+                         config_int_rows=0, comm=None, verbose=False, keep_rounds=None, wl_replicas=0, start_s_bias=None, strict=True,
+                         list_capacity=0):
     """hmc_run_program_ensemble: the reference's per-transition program (main.cc:411-491)
     for T transitions of one layer x `replicas` replicas each on THIS rank, pooled over the
     ranks of `comm`.  Returns a dict: s_bias[T][nstates], rounds[T], accepted[T], counts[T],
@@ -610,7 +620,7 @@ def run_program_ensemble(params_list, start_pos, replicas, device=0, seed=(1, 2)
                           hist_bins=int(hist_bins), dist_rows=int(dist_rows),
                           config_int_rows=int(config_int_rows), seed0=int(seed[0]) & 0xffffffff,
                           seed1=int(seed[1]) & 0xffffffff, hist_rmax=float(hist_rmax),
-                          wl_replicas=int(wl_replicas),
+                          wl_replicas=int(wl_replicas), list_capacity=int(list_capacity),
                           comm=comm.c if comm is not None else None)
     if start_s_bias is not None:
         sb0 = np.zeros((T, 16))

@@ -37,7 +37,7 @@ if __package__ in (None, ""):  # started by path, the way tools/run.py starts in
     __package__ = "hybridmc_b200"
 
 from .campaign import layers_of, run_transition_ensemble
-from .engine import Comm, EnsembleError, init_pos_chain
+from .engine import ERR_LIST_OVERFLOW, Comm, init_pos_chain
 from .output import File, write_hdf5
 from .params import transition_jsons
 
@@ -82,11 +82,14 @@ def layer_replicas(replicas, n_transitions, world=1, fill=0):
 def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, max_rounds=40,
                  max_layers=None, hist_bins=2048, rank=0, world=1, log=print, wl=True,
                  eq_iters=None, seed_increment=1, stair_bp=None, stair_rc=None, comm=None,
-                 fill=0, dist_rows=None, config_int_rows=None, keep_rounds=4, wl_replicas=0, warm_start=False):
+                 fill=0, dist_rows=None, config_int_rows=None, keep_rounds=4, wl_replicas=0, warm_start=False, restart=None):
     """stair_bp / stair_rc: init_json.py's --bp / --rc — the transitions that form bond
     `stair_bp` run as a sequence of stages with shrinking rc, each started from the previous
     stage's structure; stage j of all of a layer's staircase transitions is one ensemble.
     `replicas`: per transition, summed over the ranks of `comm`.
+    restart: path of a `restart.npz` written by an earlier (interrupted) run of the same
+    campaign: its finished layers are skipped and their hand-off structures / s_bias values
+    are taken from the file (the per-transition .h5 files of those layers need not exist).
     warm_start: a transition that forms bond b on top of the bonds B starts its
     flat-histogram iteration from the converged s_bias of "b on top of B minus one bond" of
     the previous layer (the smallest of those values: an estimate that is too low climbs
@@ -101,12 +104,25 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
     rmax = master["length"] * 0.5 * 3 ** 0.5
     stair_bp = sorted(stair_bp) if stair_bp is not None else None
     summary = []
+    n_written = 0
     events = 0
     s_est = {}  # (bits_in, bits_out) -> converged s_bias[0], for warm_start
+    layers_done = -1
+    if restart:
+        z = np.load(restart)
+        layers_done = int(z["layers_done"])
+        unbits = lambda t: tuple(c == "1" for c in t)  # noqa: E731
+        for key, pos in zip(z["state_bits"].tolist(), z["state_pos"]):
+            structures[unbits(key)] = pos
+        for bi, bo, v in zip(z["est_in"].tolist(), z["est_out"].tolist(), z["est_val"].tolist()):
+            s_est[(unbits(bi), unbits(bo))] = v
+        log("restart: layers 0..%d taken from %s (%d structures)" % (layers_done, restart, len(structures)))
     t_start = time.time()
     for layer, trans in layers:
         if max_layers is not None and layer >= max_layers:
             break
+        if layer <= layers_done:
+            continue
         mine = list(range(len(trans)))
         # jobs[k] = the stages of transition k: [(params, json, output name)]
         jobs = {}
@@ -144,6 +160,7 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                     todo + [-1] * (len(mine) - len(todo)), dtype=np.int64)) if k >= 0]
             if not todo:
                 continue
+            list_cap = 0
             for attempt in range(3):
                 params = [jobs[k][stage][0] for k in todo]
                 p0 = params[0]
@@ -178,14 +195,20 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                     max_rounds=max_rounds, hist_bins=hist_bins, hist_rmax=rmax, wl=wl,
                     eq_iters=eq_iters, comm=comm, dist_rows=rows, config_int_rows=cfgs,
                     keep_rounds=keep_rounds, wl_replicas=wl_replicas, start_s_bias=start_sb,
-                    strict=False)
+                    strict=False, list_capacity=list_cap)
                 # a transition stopped by a replica error flag: the reference's process dies with
                 # an exception there (main.cc:48-56,219-225) and tools/rerun.py runs it again;
                 # nothing of it is written, the loop below comes back to it with another seed
                 failed = [k for n, k in enumerate(todo) if out["failed"][n]]
                 if failed:
-                    log("layer %d: replica error flags in %s (attempt %d)" % (
-                        layer, [(jobs[k][stage][2], int(out["err"][todo.index(k)])) for k in failed], attempt))
+                    if rank == 0:
+                        log("layer %d: replica error flags in %s (attempt %d)" % (
+                            layer, [(jobs[k][stage][2], int(out["err"][todo.index(k)])) for k in failed],
+                            attempt))
+                    if any(int(out["err"][todo.index(k)]) & ERR_LIST_OVERFLOW for k in failed):
+                        # a compact state holds more live predictions than the default list:
+                        # 8 per bead next, then every nonlocal pair (cannot overflow)
+                        list_cap = 8 * p0.nbeads if attempt == 0 else p0.nbeads * p0.nbeads
                 dt = time.time() - t0
                 events += int(out["events"][0])
                 for n, k in enumerate(todo):
@@ -238,6 +261,11 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                             R * world, out["rounds"][n], bool(out["accepted"][n]),
                             out["s_bias"][n].tolist(), out["counts"][n].tolist(), int(out["err"][n])))
                 if rank == 0:
+                    # tools/diff_s_bias.py:72-74 rows, appended batch by batch (an interrupted
+                    # campaign keeps what it has)
+                    with open(os.path.join(out_dir, "diff_s_bias.csv"), "a", newline="") as f:
+                        csv.writer(f).writerows(summary[n_written:])
+                    n_written = len(summary)
                     log("layer %d%s: %d transitions, %d replicas each%s, rounds %s, %.1f s (%.1f s device), "
                         "events %d, collectives %d" % (
                             layer, " stage %d" % stage if stage else "", len(todo), R * world,
@@ -255,9 +283,16 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
         missing = [t[1] for lt in layers[layer + 1:layer + 2] for t in lt[1] if t[0] not in structures]
         if missing:
             raise RuntimeError("layer %d produced no structure for %d states" % (layer, len(set(missing))))
-    if rank == 0:
-        with open(os.path.join(out_dir, "diff_s_bias.csv"), "a", newline="") as f:
-            csv.writer(f).writerows(summary)  # tools/diff_s_bias.py:72-74
+        if rank == 0:  # what a later run needs to go on from here (see `restart`)
+            keys = list(structures)
+            est = list(s_est.items())
+            tmp = os.path.join(out_dir, "restart.tmp.npz")
+            np.savez_compressed(tmp, layers_done=layer, state_bits=np.array([fmt(k) for k in keys]),
+                                state_pos=np.array([structures[k] for k in keys]),
+                                est_in=np.array([fmt(k[0]) for k, _ in est]),
+                                est_out=np.array([fmt(k[1]) for k, _ in est]),
+                                est_val=np.array([v for _, v in est], dtype=np.float64))
+            os.replace(tmp, os.path.join(out_dir, "restart.npz"))
     return summary, time.time() - t_start, events
 
 
@@ -292,6 +327,8 @@ def main(argv=None):
     ap.add_argument("--no-wl", action="store_true", help="skip the per-replica Wang-Landau pre-estimate")
     ap.add_argument("--eq-iters", type=int, default=None)
     ap.add_argument("--hist-bins", type=int, default=2048)
+    ap.add_argument("--restart", default=None,
+                    help="restart.npz of an interrupted run: skip its finished layers")
     ap.add_argument("--warm-start", action="store_true",
                     help="start s_bias from the same bond's converged value one layer earlier")
     ap.add_argument("--wl-replicas", type=int, default=0,
@@ -324,7 +361,7 @@ def main(argv=None):
         args.max_layers, hist_bins=args.hist_bins, rank=rank, world=world, wl=not args.no_wl,
         eq_iters=args.eq_iters, seed_increment=args.seed_increment, stair_bp=args.bp,
         stair_rc=args.rc, comm=comm, fill=fill, dist_rows=args.dist_rows,
-        config_int_rows=args.config_int_rows, wl_replicas=args.wl_replicas, warm_start=args.warm_start)
+        config_int_rows=args.config_int_rows, wl_replicas=args.wl_replicas, warm_start=args.warm_start, restart=args.restart)
     if rank == 0:
         print("%d transitions on %d GPU(s) in %.1f s -> %.0f transitions/hour, %.3e collision "
               "events (%.3e events/s whole campaign)" % (

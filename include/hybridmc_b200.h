@@ -426,6 +426,15 @@ int hmc_comm_allreduce_device_u64(hmc_comm c, void *dptr, uint64_t n, void *cuda
  * indices (first = 0, total = replicas_per_transition). */
 int hmc_set_replica_ids(hmc_handle h, unsigned first, unsigned total_per_transition);
 
+/* Capacity (entries) of a replica's list of live nonlocal predictions in shared memory.
+ * The default keeps 16 warps per SM resident and covers open chains with a wide margin; a
+ * compact state (most bonds of a protein formed) can hold more, which raises
+ * HMC_ERR_LIST_OVERFLOW: run it again with a larger list (fewer replicas per SM).  Every
+ * nonlocal pair plus two beads' worth is the most a list can hold; larger values are clipped.
+ * 0: default.  Takes effect at the next launch (the list lives only within a launch). */
+int hmc_set_list_capacity(hmc_handle h, unsigned entries);
+unsigned hmc_get_list_capacity(hmc_handle h);
+
 /* ---- independent-program mode ----------------------------------------------------------
  * Every replica keeps its own s_bias and its own config_count, i.e. runs the reference's
  * whole program like one CPU process with its own seed (R replicas = R reference seeds
@@ -466,6 +475,8 @@ typedef struct hmc_ensemble_options {
                                of the device time */
   double hist_rmax;
   hmc_comm comm;            /* NULL: one rank */
+  uint32_t list_capacity;   /* hmc_set_list_capacity; 0: default */
+  uint32_t pad2;
   const double *start_s_bias; /* NULL: init_s (entropy.cc:14-20); else [T][16] start values
                                of the flat-histogram iteration, e.g. the converged value of
                                the same bond one lattice layer earlier (fewer rounds) */
@@ -526,6 +537,10 @@ int hmc_get_launch_stats(hmc_handle h, uint64_t *n_launches, float *last_ms);
  * x replicas per warp): ensembles smaller than this leave SMs idle, so a campaign tops thin
  * lattice layers up to it.  <0: no such device. */
 int hmc_resident_replicas(unsigned nbeads, int device);
+/* Debug builds (-DHMC_DEBUG_BOUNDS, libhybridmc_b200_bounds.so): out-of-range indices into
+ * the shared-memory replica image counted so far on the current device.  -1: this library is
+ * not such a build. */
+long long hmc_debug_bounds_violations(void);
 /* Interval timer on the handle's stream (CUDA events): everything enqueued between the two
  * calls — kernels, the NCCL all-reduce of hmc_allreduce_counts, copies — and the host gaps
  * between them.  hmc_timer_stop synchronises and returns the milliseconds. */

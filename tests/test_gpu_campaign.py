@@ -102,3 +102,49 @@ def test_staircase_sweep_layer0(tmp_path):
             dd = pos[bp[1]] - pos[bp[0]]
             dd -= master["length"] * np.round(dd / master["length"])
             assert np.linalg.norm(dd) < rc
+
+
+def test_restart_pack_continues_without_the_earlier_files(tmp_path):
+    """restart.npz (written after every layer) carries the hand-off structures and s_bias
+    values: a second run continues with the next layer although the per-transition files of
+    the finished layer are gone (a campaign interrupted on a machine whose disk is lost)"""
+    master = load_config("test")
+    out = str(tmp_path / "camp")
+    kw = dict(replicas=48, iters_per_round=2, max_rounds=2, hist_bins=256, wl=False, eq_iters=2,
+              log=lambda *a: None, warm_start=True)
+    s1, _, _ = run_campaign(master, out, max_layers=1, **kw)
+    assert len(s1) == 3 and os.path.exists(os.path.join(out, "restart.npz"))
+    with open(os.path.join(out, "diff_s_bias.csv")) as f:
+        assert len(list(csv.reader(f))) == 3
+    out2 = str(tmp_path / "camp2")
+    os.makedirs(out2)
+    s2, _, _ = run_campaign(master, out2, max_layers=2, restart=os.path.join(out, "restart.npz"), **kw)
+    assert len(s2) == 6 and all(r[0].count("1") == 1 for r in s2)
+    names = sorted(f for f in os.listdir(out2) if f.endswith(".h5"))
+    assert len(names) == 6 and all(n.startswith("hybridmc_1_") for n in names)
+
+
+def test_list_capacity_overflow_is_flagged_and_curable():
+    """HMC_ERR_LIST_OVERFLOW: a list of live nonlocal predictions that is too small raises the
+    flag (the replica's trajectory is then void); the default capacity and a larger one do
+    not, and give identical trajectories (the capacity is not part of the arithmetic)"""
+    from common import transition_params
+    from hybridmc_b200.engine import ERR_LIST_OVERFLOW, PHASE_MAIN, Engine, init_pos_chain
+    p = transition_params("crambin", 0)
+    pos = init_pos_chain(p)
+    outs = []
+    for cap in (8, 0, 1000):
+        with Engine(p, 6) as e:
+            e.set_list_capacity(cap)
+            assert e.get_list_capacity() >= 8
+            e.set_positions(np.broadcast_to(pos, (6,) + pos.shape))
+            e.init_config_from_positions()
+            e.init_s()
+            e.seed(5, 6)
+            e.reset_clocks()
+            e.run(PHASE_MAIN, 0, 1)
+            err = int(np.bitwise_or.reduce(e.get_counts()[3]))
+            outs.append((err, e.get_positions().copy()))
+    assert outs[0][0] & ERR_LIST_OVERFLOW
+    assert outs[1][0] == 0 and outs[2][0] == 0
+    assert np.array_equal(outs[1][1].view(np.uint64), outs[2][1].view(np.uint64))
