@@ -90,6 +90,25 @@ def run_transition_ensemble(params_list, start_pos, replicas, device=0, seed=(1,
                                 comm=comm, **kw)
 
 
+def stair_entropy(stage_s_bias):
+    """Entropy difference of a staircase transition from the s_bias[0] of its stages, as
+    tools/diff_s_bias_stair.py:47-58 combines them: log of the sum of exp(sum of subset)
+    over all non-empty subsets of the stage values = log(prod(1 + e^v) - 1)."""
+    v = np.asarray(stage_s_bias, dtype=np.float64)
+    return float(np.log(np.prod(1.0 + np.exp(v)) - 1.0))
+
+
+def collect_stair(rows):
+    """diff_s_bias.csv rows (bits_in, bits_out[_rc], s) -> {(bits_in, bits_out): value}: plain
+    transitions keep their value, the stages of a staircase transition are combined with
+    stair_entropy (tools/diff_s_bias_stair.py:20-58)."""
+    stages = {}
+    for bits_in, tail, s in rows:
+        bits_out = tail.split("_")[0]
+        stages.setdefault((bits_in, bits_out), []).append(float(s))
+    return {k: (v[0] if len(v) == 1 else stair_entropy(v)) for k, v in stages.items()}
+
+
 # ---- multi-GPU: one process per GPU, shard + one all-reduce per G-test round ----------
 
 def shard(n_items, rank, world):

@@ -79,6 +79,25 @@ def layer_replicas(replicas, n_transitions, world=1, fill=0):
     return per_rank
 
 
+def warm_start_guess(s_est, bits_in, bits_out):
+    """Start value of s_bias[0] for the transition bits_in -> bits_out (it forms bond b):
+    the smallest converged value of "b on top of bits_in minus one bond" among the
+    transitions of the previous layer found in s_est {(bits_in, bits_out): s_bias[0]};
+    None if there is none (layer 0).  The smallest, because the flat-histogram iteration
+    climbs quickly from an estimate that is too low (+0.5 ln(c0/c1) per round) but descends
+    slowly from one that is too high (-neg_scale ln(norm) while the open state is never
+    visited, entropy.cc:46-63)."""
+    new = [i for i in range(len(bits_in)) if bits_in[i] != bits_out[i]][0]
+    guesses = []
+    for c in range(len(bits_in)):
+        if bits_in[c]:
+            pi = tuple(bool(x) and i != c for i, x in enumerate(bits_in))
+            po = tuple(x or i == new for i, x in enumerate(pi))
+            if (pi, po) in s_est:
+                guesses.append(s_est[(pi, po)])
+    return min(guesses) if guesses else None
+
+
 def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, max_rounds=40,
                  max_layers=None, hist_bins=2048, rank=0, world=1, log=print, wl=True,
                  eq_iters=None, seed_increment=1, stair_bp=None, stair_rc=None, comm=None,
@@ -178,16 +197,8 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                 if warm_start and p0.nstates == 2:
                     start_sb = np.zeros((len(todo), 2))
                     for n, k in enumerate(todo):
-                        b_in, b_out = trans[k][0], trans[k][1]
-                        new = [i for i in range(nb_bonds) if b_in[i] != b_out[i]][0]
-                        guesses = []
-                        for c in range(nb_bonds):
-                            if b_in[c]:
-                                pi = tuple(x and i != c for i, x in enumerate(b_in))
-                                po = tuple(x or i == new for i, x in enumerate(pi))
-                                if (pi, po) in s_est:
-                                    guesses.append(s_est[(pi, po)])
-                        start_sb[n, 0] = min(guesses) if guesses and stage == 0 else 3.0
+                        g = warm_start_guess(s_est, trans[k][0], trans[k][1]) if stage == 0 else None
+                        start_sb[n, 0] = 3.0 if g is None else g
                 t0 = time.time()
                 out = run_transition_ensemble(
                     params, [stage_pos[k] for k in todo], R, device=device,

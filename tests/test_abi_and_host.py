@@ -162,3 +162,31 @@ def test_stair_stages_follow_init_json():
     assert st[1][0]["stair_bonds"] == [[4, 16]] and all("p_rc" not in x for x, _ in st)
     st1 = stair_stages(dict(d, permanent_bonds=[[2, 6]]), 1, 1.5, [3.0, 1.5])
     assert all(x["p_rc"] == 1.5 for x, _ in st1) and d["rc"] == 1.5 and "stair" not in d
+
+
+def test_stair_entropy_combination():
+    """tools/diff_s_bias_stair.py:47-58: all non-empty subsets of the stage values"""
+    from itertools import combinations
+    from hybridmc_b200.campaign import collect_stair, stair_entropy
+    v = [2.1, 0.7, 1.3]
+    ref = np.log(sum(np.exp(sum(c)) for i in range(1, 4) for c in combinations(v, i)))
+    assert abs(stair_entropy(v) - ref) < 1e-12
+    rows = [("000", "100_3.0", 2.1), ("000", "100_2.2", 0.7), ("000", "100", 1.3), ("000", "010", 3.5)]
+    out = collect_stair(rows)
+    assert abs(out[("000", "100")] - ref) < 1e-12 and out[("000", "010")] == 3.5
+
+
+def test_campaign_host_logic():
+    """layer_replicas (replica split + topping thin layers up) and the warm-start guess"""
+    from hybridmc_b200.run_campaign import layer_replicas, warm_start_guess
+    assert layer_replicas(64, 1260, world=8) == 8
+    assert layer_replicas(64, 10, world=1, fill=4736) == 474      # thin layer topped up
+    assert layer_replicas(64, 10, world=2, fill=4736) == 474      # per rank
+    assert layer_replicas(64, 1260, world=2, fill=4736) == 32     # fat layer: the nominal split
+    assert layer_replicas(65, 4, world=8) == 9                    # rounded up
+    T, F = True, False
+    est = {((F, F, F), (T, F, F)): 9.4, ((F, T, F), (T, T, F)): 2.0, ((F, F, T), (T, F, T)): 8.8}
+    assert warm_start_guess(est, (F, F, F), (T, F, F)) is None                 # layer 0
+    assert warm_start_guess(est, (F, T, F), (T, T, F)) == 9.4                  # one predecessor
+    # bond 0 on top of {1, 2}: predecessors remove bond 1 (-> 8.8) or bond 2 (-> 2.0): the smaller
+    assert warm_start_guess(est, (F, T, T), (T, T, T)) == 2.0
