@@ -398,6 +398,18 @@ def run_gpu_arm(args):
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        # HBM side of a launch: every replica's snapshot (positions in and out, velocities out,
+        # bond state, s_bias row, error word) crosses HBM once per launch, the per-state
+        # counts / histograms are a handful of atomics per recorded sample.  Algorithmic bytes
+        # per launch over the measured launch duration = the HBM bandwidth the path needs.
+        nbeads = int(params[0].nbeads)
+        state_bytes = R * len(params) * (3 * 24 * nbeads + 2 * 8 + 16 + 2 * 4)
+        ker_s = float(sum(kernel_ms)) * 1e-3 / max(len(kernel_ms), 1)
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -427,6 +439,14 @@ def run_gpu_arm(args):
                                  "ceiling of a -fmad=false kernel; DFMA rate %.1f TFLOP/s); achieved = "
                                  "kernel-only events/s of one GPU x %.0f algorithmic FP64 ops per event; "
                                  "MEASURED_PEAKS.json has no FP64 entry" % (fma_tf, kflop)},
+            "hbm": {"snapshot_bytes_per_launch": state_bytes,
+                    "snapshot_GBps_needed": state_bytes / ker_s * 1e-9,
+                    "ncu_dram_bytes_per_launch": traffic,
+                    "ncu_dram_GBps": (traffic / ker_s * 1e-9) if traffic else None,
+                    "hbm_peak_GBps_measured": hbm_peak,
+                    "note": "replica state lives in shared memory for the whole launch; HBM sees one "
+                            "snapshot read + write per replica and launch plus count/histogram atomics "
+                            "(measured peak copy bandwidth of this pool: MEASURED_PEAKS.json)"},
             "clocks": clocks_summary(clk_path),
         }
         if campaign is not None:

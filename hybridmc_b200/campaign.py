@@ -109,6 +109,29 @@ def collect_stair(rows):
     return {k: (v[0] if len(v) == 1 else stair_entropy(v)) for k, v in stages.items()}
 
 
+def state_entropies(nbonds, diffs):
+    """Per-state entropies from per-transition differences, as tools/avg_s_bias.py:36-72 forms
+    them: S(all bonds formed) = 0; walking the lattice one broken bond at a time, the entropy
+    of a state is the MEAN over the bonds b it lacks of  S(state + b) + diff[(state, state + b)]
+    (each parent's own mean is final before its children are visited, because a layer is
+    complete before the next one starts).  diffs: {(bits_in, bits_out): s_bias[0]} with bit
+    strings; returns {bits: S}."""
+    full = "1" * nbonds
+    S = {full: 0.0}
+    layer = [full]
+    while layer:
+        acc = {}
+        for parent in layer:
+            for b in range(nbonds):
+                if parent[b] == "1":
+                    child = parent[:b] + "0" + parent[b + 1:]
+                    acc.setdefault(child, []).append(diffs[(child, parent)] + S[parent])
+        for child, vals in acc.items():
+            S[child] = float(np.mean(vals))
+        layer = sorted(acc)
+    return S
+
+
 # ---- multi-GPU: one process per GPU, shard + one all-reduce per G-test round ----------
 
 def shard(n_items, rank, world):

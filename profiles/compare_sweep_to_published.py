@@ -26,6 +26,22 @@ for layer in sorted(by_layer):
                                                    np.abs(d).max(), np.corrcoef(a[:, 0], a[:, 1])[0, 1] if len(a) > 2 else 1))
 d = np.concatenate(alld)
 print("%5s %6d %10.4f %10.4f %10.4f" % ("all", len(d), d.mean(), d.std(ddof=1), np.abs(d).max()))
+if len(rows) == 5120:
+    sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+    from hybridmc_b200.campaign import state_entropies
+    mine_S = state_entropies(10, {(r[0], r[1]): float(r[2]) for r in rows})
+    keys = sorted(S)
+    a = np.array([mine_S[k] for k in keys])
+    b = np.array([S[k] for k in keys])
+    nb_ = np.array([k.count("1") for k in keys])
+    print("\nper-state entropies (tools/avg_s_bias.py path average) vs published s_bias.csv, %d states" % len(keys))
+    print("%7s %5s %10s %10s %10s" % ("bonds", "n", "mean diff", "sd diff", "max |diff|"))
+    for k_ in range(11):
+        m = nb_ == k_
+        dd = (a - b)[m]
+        print("%7d %5d %10.4f %10.4f %10.4f" % (k_, m.sum(), dd.mean(), dd.std(ddof=1) if m.sum() > 1 else 0, np.abs(dd).max()))
+    print("S(no bonds): %.3f vs published %.3f; corr %.5f; rms diff %.4f" % (
+        mine_S["0" * 10], S["0" * 10], np.corrcoef(a, b)[0, 1], np.sqrt(np.mean((a - b) ** 2))))
 if len(sys.argv) > 2:
     pub = {(r[0], r[1]): (float(r[3]), float(r[4])) for r in list(csv.reader(open(PUB + "mfpt.csv")))[1:]}
     mine = {(r[0], r[1]): (float(r[3]), float(r[4])) for r in list(csv.reader(open(sys.argv[2])))[1:]}

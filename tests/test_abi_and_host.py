@@ -190,3 +190,12 @@ def test_campaign_host_logic():
     assert warm_start_guess(est, (F, T, F), (T, T, F)) == 9.4                  # one predecessor
     # bond 0 on top of {1, 2}: predecessors remove bond 1 (-> 8.8) or bond 2 (-> 2.0): the smaller
     assert warm_start_guess(est, (F, T, T), (T, T, T)) == 2.0
+
+
+def test_state_entropies_match_avg_s_bias_semantics():
+    """tools/avg_s_bias.py on a 2-bond lattice worked by hand: S(11) = 0; S(01) = d(01->11);
+    S(10) = d(10->11); S(00) = mean(S(01) + d(00->01), S(10) + d(00->10))"""
+    from hybridmc_b200.campaign import state_entropies
+    d = {("01", "11"): 2.0, ("10", "11"): 3.0, ("00", "01"): 4.0, ("00", "10"): 3.5}
+    S = state_entropies(2, d)
+    assert S == {"11": 0.0, "01": 2.0, "10": 3.0, "00": (6.0 + 6.5) / 2}
