@@ -126,6 +126,7 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
     n_written = 0
     events = 0
     s_est = {}  # (bits_in, bits_out) -> converged s_bias[0], for warm_start
+    list_cap_floor = 0
     layers_done = -1
     if restart:
         z = np.load(restart)
@@ -179,7 +180,9 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                     todo + [-1] * (len(mine) - len(todo)), dtype=np.int64)) if k >= 0]
             if not todo:
                 continue
-            list_cap = 0
+            # (sticky: once a layer needed a larger list the deeper, more compact ones start
+            # with it instead of running their overflowing transitions twice)
+            list_cap = list_cap_floor
             for attempt in range(3):
                 params = [jobs[k][stage][0] for k in todo]
                 p0 = params[0]
@@ -219,7 +222,8 @@ def run_campaign(master, out_dir, replicas=512, device=0, iters_per_round=None, 
                     if any(int(out["err"][todo.index(k)]) & ERR_LIST_OVERFLOW for k in failed):
                         # a compact state holds more live predictions than the default list:
                         # 8 per bead next, then every nonlocal pair (cannot overflow)
-                        list_cap = 8 * p0.nbeads if attempt == 0 else p0.nbeads * p0.nbeads
+                        list_cap = 8 * p0.nbeads if list_cap < 8 * p0.nbeads else p0.nbeads * p0.nbeads
+                        list_cap_floor = max(list_cap_floor, 8 * p0.nbeads)
                 dt = time.time() - t0
                 events += int(out["events"][0])
                 for n, k in enumerate(todo):
