@@ -39,10 +39,21 @@ def _quadrature(x_knot, order=24):
     return nodes.ravel(), weights.ravel()
 
 
-def fit_pmf(x, weights, lo, hi, nknots=NKNOTS):
+REFERENCE_TOL = 5e-5  # tools/minimize.py:26-30: ftol_rel = xtol_rel = 5e-5
+
+
+def fit_pmf(x, weights, lo, hi, nknots=NKNOTS, reference_tolerance=False):
     """Maximum-likelihood knot ordinates y of -ln p(r) on [lo, hi] for data points x
     with weights (sample: weights = 1; histogram: bin centres and counts).
-    Returns (x_knot, y)."""
+    Returns (x_knot, y).
+
+    reference_tolerance: an experiment switch — L-BFGS from the flat start y = 0
+    (tools/mfpt.py:376) ended by nlopt's relative tolerances as tools/minimize.py:26-30 sets
+    them: the first iterate whose step changed the objective by less than 5e-5 |f| or every
+    ordinate by less than 5e-5 |y_i|.  With scipy's L-BFGS path this rule stops close to the
+    maximum-likelihood fit (profiles/long_loop_reference_tolerance.py: the long-loop outer
+    times stay 2.2x the published ones), so the stopping rule alone does not explain the
+    published long-loop values; nlopt's own iterates cannot be reproduced here."""
     x_knot = np.linspace(lo, hi, nknots)
     w = np.asarray(weights, dtype=float)
     w = w / w.sum()
@@ -57,6 +68,19 @@ def fit_pmf(x, weights, lo, hi, nknots=NKNOTS):
         z = e.sum()
         return bw @ y + np.log(z) + m, bw - (bq.T @ e) / z
 
+    if reference_tolerance:
+        path = [np.zeros(nknots)]
+        optimize.minimize(f_df, np.zeros(nknots), jac=True, method="L-BFGS-B",
+                          callback=lambda xk: path.append(np.array(xk)),
+                          options=dict(maxiter=200, ftol=1e-13, gtol=1e-9))
+        f_prev = f_df(path[0])[0]
+        for k in range(1, len(path)):
+            f_k = f_df(path[k])[0]
+            dy = np.abs(path[k] - path[k - 1])
+            if abs(f_k - f_prev) < REFERENCE_TOL * abs(f_k) or np.all(dy < REFERENCE_TOL * np.abs(path[k])):
+                return x_knot, path[k]
+            f_prev = f_k
+        return x_knot, path[-1]
     res = optimize.minimize(f_df, np.zeros(nknots), jac=True, method="L-BFGS-B",
                             options=dict(maxiter=2000, ftol=1e-13, gtol=1e-9))
     return x_knot, res.x
@@ -97,7 +121,7 @@ def fpt_from_samples(dist, lo, hi, inner, nknots=NKNOTS):
     return fpt_from_fit(xk, y, inner)
 
 
-def fpt_from_hist(counts, rmax, lo, hi, inner, nknots=NKNOTS):
+def fpt_from_hist(counts, rmax, lo, hi, inner, nknots=NKNOTS, reference_tolerance=False):
     """The same from a histogram of `len(counts)` equal bins over [0, rmax) (binned
     likelihood: every sample sits at its bin centre).  Bins are clipped to [lo, hi]; for
     the outer time hi=None means "up to the last occupied bin" (mfpt.py:137: max(t_off))."""
@@ -111,8 +135,20 @@ def fpt_from_hist(counts, rmax, lo, hi, inner, nknots=NKNOTS):
     sel = (centres >= lo) & (centres <= hi) & (counts > 0)
     if sel.sum() < 4:
         raise ValueError("too few occupied bins in [%g, %g]" % (lo, hi))
-    xk, y = fit_pmf(centres[sel], counts[sel], lo, hi, nknots)
+    xk, y = fit_pmf(centres[sel], counts[sel], lo, hi, nknots, reference_tolerance)
     return fpt_from_fit(xk, y, inner)
+
+
+def fpt_hist_bootstrap(counts, rmax, lo, hi, inner, nboot, seed=0, nknots=NKNOTS):
+    """Variance of the histogram estimate by the reference's bootstrap (tools/mfpt.py:383-395:
+    `nboot` resamples of HALF the sample size, with replacement): resampling n/2 of the n
+    binned distances is a multinomial draw over the bins."""
+    c = np.asarray(counts, dtype=np.int64)
+    n = int(c.sum())
+    rng = np.random.default_rng(seed)
+    vals = [fpt_from_hist(rng.multinomial(n // 2, c / n), rmax, lo, hi, inner, nknots)
+            for _ in range(nboot)]
+    return float(np.var(vals, ddof=1))
 
 
 def transition_fpts(hist, rmax, params, bond_column=None):
@@ -169,6 +205,10 @@ def fpt_rows(data, dist=None, hist=None, rmax=None, nboot=0, seed=0):
             row = [i, fpt_from_hist(h[1], rmax, rh, rc, True) if i == t_ind else
                    fpt_from_hist(h[1], rmax, rc, None, False),
                    fpt_from_hist(h[0], rmax, rc, None, False)]
+            if nboot > 1:
+                row += [fpt_hist_bootstrap(h[1], rmax, rh if i == t_ind else rc,
+                                           rc if i == t_ind else None, i == t_ind, nboot, seed),
+                        fpt_hist_bootstrap(h[0], rmax, rc, None, False, nboot, seed)]
         rows.append(row)
     return rows
 
@@ -195,7 +235,8 @@ def main(argv=None):
             print("number of distances =", len(f["dist"]))
             rows = fpt_rows(data, dist=f["dist"], nboot=args.nboot)
         else:
-            rows = fpt_rows(data, hist=f["dist_hist"], rmax=float(f.attrs["dist_hist_rmax"]))
+            rows = fpt_rows(data, hist=f["dist_hist"], rmax=float(f.attrs["dist_hist_rmax"]),
+                            nboot=args.nboot)
     with open(args.csv, "w", newline="") as f:
         csv.writer(f).writerows(rows)
 

@@ -113,6 +113,9 @@ def test_independent_programs_match_reference_distribution_2_sigma():
     r_sem = np.hypot(rounds.std(ddof=1) / np.sqrt(len(rounds)), cpu[:, 1].std(ddof=1) / np.sqrt(len(cpu)))
     assert abs(rounds.mean() - cpu[:, 1].mean()) < 2 * r_sem + 1e-12, (rounds.mean(), cpu[:, 1].mean(), r_sem)
     assert np.allclose(out["s_bias"][0][0], g_mean)
+    # the two samples of single-run estimates come from one distribution (Kolmogorov-Smirnov)
+    from scipy import stats
+    assert stats.ks_2samp(sb[:, 0], cpu[:, 0]).pvalue > 0.01
 
 
 def test_pooled_estimate_within_2_sigma_of_reference_mean():
@@ -260,6 +263,29 @@ def test_executable_ensemble_mode(tmp_path):
         assert f["dist_hist"].shape == (1, 2, 512)
         assert len(f["unique_config"]["pos"]) == 1
         assert len(f["config"]["int"]) > 0
+
+
+def test_concurrent_executables_share_one_gpu(tmp_path):
+    """tools/init_json.py --nproc N starts N executables at once (multiprocessing pool,
+    init_json.py:14-36): several `hybridmc --replicas` processes on ONE GPU must all finish
+    with valid, different-seed results"""
+    from hybridmc_b200.output import File
+    exe = _exe()
+    procs = []
+    for k in range(3):
+        d = load_config("8bead_1bond", seeds=[11 + k, 1])
+        jpath, opath = str(tmp_path / ("t%d.json" % k)), str(tmp_path / ("t%d.h5" % k))
+        with open(jpath, "w") as f:
+            json.dump(d, f)
+        procs.append((subprocess.Popen([exe, jpath, opath, "--replicas", "128", "--iters-per-round", "4"],
+                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True), opath))
+    vals = []
+    for pr, opath in procs:
+        _, err = pr.communicate(timeout=600)
+        assert pr.returncode == 0, err
+        with File(opath) as f:
+            vals.append(float(f["s_bias"][0]))
+    assert all(abs(v - 3.6) < 0.4 for v in vals) and len(set(vals)) == 3
 
 
 _RANK_SCRIPT = r"""

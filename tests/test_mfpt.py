@@ -89,3 +89,21 @@ def test_command_line_matches_the_reference_tools_layout(tmp_path):
     on = d_o[(d_t < rc) & (d_o >= rc)]
     assert rows[0][1] == pytest.approx(mfpt.fpt_from_samples(on, rc, on.max(), False), rel=1e-9)
     assert all(np.isfinite(r[1]) and r[1] > 0 and r[2] > 0 for r in rows)
+
+
+def test_histogram_bootstrap_variance_matches_repeated_sampling():
+    """fpt_hist_bootstrap (the reference's half-sample bootstrap, tools/mfpt.py:383-395, as a
+    multinomial draw over the bins): its variance is that of an estimate from n/2 samples,
+    i.e. about twice the variance seen over independent full-size histograms"""
+    rng = np.random.default_rng(11)
+    lo, hi, rmax, n = 1.25, 1.5, 8.0, 40000
+
+    def sample():
+        x = rng.uniform(lo, hi, 3 * n)
+        return x[rng.uniform(0, hi * hi, x.size) < x * x][:n]
+    hists = [np.histogram(sample(), bins=2048, range=(0, rmax))[0] for _ in range(10)]
+    vals = [mfpt.fpt_from_hist(h, rmax, lo, hi, True) for h in hists]
+    boot = mfpt.fpt_hist_bootstrap(hists[0], rmax, lo, hi, True, nboot=12, seed=1)
+    assert boot > 0
+    ratio = boot / (2 * np.var(vals, ddof=1))
+    assert 0.2 < ratio < 5.0, ratio
