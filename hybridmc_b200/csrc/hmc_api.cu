@@ -92,9 +92,15 @@ int fail(hmc_handle h, const std::string &msg, int code = -1) {
       return fail(h, std::string(#call) + ": " + cudaGetErrorString(e_), -2);            \
   } while (0)
 
+// Zero-initialised device buffer.  cudaMemset runs on the legacy default stream and is
+// asynchronous to the host, while the engine's stream is NON-BLOCKING (no implicit ordering
+// with the default stream): without the synchronisation below the zeroing can overtake — and
+// wipe — the first upload on the engine's stream (seen when several processes share a GPU:
+// tests/test_gpu_program_ensemble.py::test_concurrent_executables_share_one_gpu).
 template <class T> cudaError_t dalloc(T **p, size_t n) {
   cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), n * sizeof(T));
   if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
   return e;
 }
 
