@@ -898,9 +898,10 @@ int hmc_enable_samples(hmc_handle h, unsigned dist_rows, unsigned cfg_cap) {
     if (!h->d_cfg_n) CK(dalloc(&h->d_cfg_n, size_t(h->R)));
     h->cfg_cap = cfg_cap;
   }
-  if (h->d_dist_n) CK(cudaMemset(h->d_dist_n, 0, sizeof(uint32_t) * h->R));
-  if (h->d_cfg_n) CK(cudaMemset(h->d_cfg_n, 0, sizeof(uint32_t) * h->R));
-  return 0;
+  // (on the engine's stream: a default-stream memset is not ordered with it, see dalloc)
+  if (h->d_dist_n) CK(cudaMemsetAsync(h->d_dist_n, 0, sizeof(uint32_t) * h->R, h->stream));
+  if (h->d_cfg_n) CK(cudaMemsetAsync(h->d_cfg_n, 0, sizeof(uint32_t) * h->R, h->stream));
+  return sync(h);
 }
 
 int hmc_get_dist(hmc_handle h, double *dist, uint32_t *n_rows) {
@@ -984,7 +985,8 @@ int hmc_enable_trace(hmc_handle h, int replica, unsigned capacity) {
   h->d_trace = nullptr;
   h->trace_cap = 0;
   h->trace_replica = -1;
-  CK(cudaMemset(h->d_trace_n, 0, sizeof(uint32_t)));
+  CK(cudaMemsetAsync(h->d_trace_n, 0, sizeof(uint32_t), h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   if (capacity) {
     CK(dalloc(&h->d_trace, size_t(capacity)));
     h->trace_cap = capacity;
