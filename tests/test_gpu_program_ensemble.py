@@ -136,24 +136,24 @@ def test_pooled_estimate_within_2_sigma_of_reference_mean():
     assert abs(gpu.mean() - cpu.mean()) < 2 * sigma, (gpu.mean(), cpu.mean(), sigma)
 
 
-def test_independent_programs_layer1_of_test_json_2_sigma():
-    """the same equal-sample-count comparison on a 20-bead transition of lattice layer 1
-    (one permanent bond, start structure handed over from layer 0): 24 reference programs
-    vs 192 GPU replicas, mean s_bias within 2 sigma, no slack"""
-    from hybridmc_b200.campaign import harvest_start_structures
+@pytest.mark.parametrize("index", [0, 3, 9])
+def test_independent_programs_of_test_json_2_sigma(index):
+    """the same equal-sample-count comparison on 20-bead transitions of lattice layers 0, 1
+    and 2 (none, one, two permanent bonds; start structures: the committed fixture made by the
+    oracle): 24 reference programs vs 192 GPU replicas, mean s_bias within 2 sigma, no slack"""
     from hybridmc_b200.params import transition_jsons
     master = load_config("test")
-    layer, bits_in, bits_out, dj = transition_jsons(master)[3]
-    assert layer == 1
-    start = harvest_start_structures(master, replicas=64, seed=77)[bits_in]
+    layer, bits_in, bits_out, dj = transition_jsons(master)[index]
+    assert layer == {0: 0, 3: 1, 9: 2}[index]
+    st = np.load(os.path.join(ROOT, "tests", "golden", "start_structures_test.npz"))
+    start = np.ascontiguousarray(st["".join("1" if b else "0" for b in bits_in)])
     dj = dict(dj, total_iter=40, total_iter_eq=10)
     orc = load_oracle()
-    pin = np.ascontiguousarray(start)
 
     def one(seed):
         p = params_from_json(dict(dj, seeds=[seed, 1]))
         r = OrcMainResult()
-        assert orc.orc_run_main(C.byref(p), pin.ctypes.data_as(C.c_void_p), 3, 0, None, None,
+        assert orc.orc_run_main(C.byref(p), start.ctypes.data_as(C.c_void_p), 3, 0, None, None,
                                 C.byref(r)) == 0
         return r.s_bias[0]
     with ThreadPoolExecutor(max_workers=min(24, os.cpu_count() or 1)) as ex:
