@@ -85,6 +85,7 @@ struct hmc_comm_s {
   void *d_stage = nullptr;
   size_t stage_bytes = 0;
   uint64_t n_collectives = 0;
+  std::string id_file; // rank 0 of hmc_comm_create_from_file: removed again on destroy
 };
 
 #define NC(call)                                                                          \
@@ -162,7 +163,10 @@ int hmc_comm_create_from_file(const char *path, int rank, int world, int device,
       std::this_thread::sleep_for(std::chrono::milliseconds(20));
     }
   }
-  return hmc_comm_create(id, rank, world, device, out);
+  const int rc = hmc_comm_create(id, rank, world, device, out);
+  // (a stale id file would make the other ranks of the NEXT launch join a dead group)
+  if (rc == 0 && rank == 0) (*out)->id_file = path;
+  return rc;
 }
 
 int hmc_comm_destroy(hmc_comm c) {
@@ -172,6 +176,7 @@ int hmc_comm_destroy(hmc_comm c) {
   if (c->comm) nccl().CommDestroy(c->comm);
   if (c->d_stage) cudaFree(c->d_stage);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (!c->id_file.empty()) std::remove(c->id_file.c_str());
   delete c;
   return 0;
 }

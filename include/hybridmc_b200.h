@@ -395,7 +395,10 @@ typedef struct hmc_comm_s *hmc_comm;
 int hmc_comm_unique_id(uint8_t id[HMC_COMM_ID_BYTES]);
 int hmc_comm_create(const uint8_t id[HMC_COMM_ID_BYTES], int rank, int world, int device,
                     hmc_comm *out);
-/* the same with the id passed through a file all ranks can see (rank 0 writes it) */
+/* the same with the id passed through a file all ranks can see: rank 0 writes it (temporary
+ * file + rename), the others wait for it up to 120 s; rank 0 removes it in hmc_comm_destroy.
+ * `path` must not exist when the ranks start (a leftover of a crashed launch would be read
+ * as this launch's id): use a fresh name per launch. */
 int hmc_comm_create_from_file(const char *path, int rank, int world, int device, hmc_comm *out);
 int hmc_comm_destroy(hmc_comm c);
 int hmc_comm_rank(hmc_comm c);
