@@ -86,6 +86,7 @@ struct hmc_comm_s {
   size_t stage_bytes = 0;
   uint64_t n_collectives = 0;
   std::string id_file; // rank 0 of hmc_comm_create_from_file: removed again on destroy
+  bool borrowed = false; // hmc_comm_wrap_nccl: the ncclComm_t belongs to the caller
 };
 
 #define NC(call)                                                                          \
@@ -169,11 +170,33 @@ int hmc_comm_create_from_file(const char *path, int rank, int world, int device,
   return rc;
 }
 
+// Adopt a communicator the host already has (ncclCommInitRank / MPI-bootstrapped):
+// hmc_allreduce_counts(h, wrapped) is then SURVEY section 8(b)'s hmc_allreduce_counts(h,
+// ncclComm_t).  The ncclComm_t must belong to the libnccl.so.2 this library resolves
+// (dlopen by soname returns the copy the process has already loaded).  Not destroyed here.
+int hmc_comm_wrap_nccl(void *nccl_comm, int rank, int world, int device, hmc_comm *out) {
+  if (!nccl_comm || !out || world < 1 || rank < 0 || rank >= world)
+    return cfail("hmc_comm_wrap_nccl: bad arguments", -1);
+  *out = nullptr;
+  NcclApi &api = nccl();
+  if (!api.err.empty()) return cfail(api.err);
+  CU(cudaSetDevice(device));
+  hmc_comm c = new hmc_comm_s();
+  c->comm = static_cast<ncclComm_t>(nccl_comm);
+  c->rank = rank;
+  c->world = world;
+  c->device = device;
+  c->borrowed = true;
+  cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  *out = c;
+  return 0;
+}
+
 int hmc_comm_destroy(hmc_comm c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->comm) nccl().CommDestroy(c->comm);
+  if (c->comm && !c->borrowed) nccl().CommDestroy(c->comm);
   if (c->d_stage) cudaFree(c->d_stage);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (!c->id_file.empty()) std::remove(c->id_file.c_str());

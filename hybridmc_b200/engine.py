@@ -41,6 +41,7 @@ EXPORTS = [
     "hmc_set_s_bias_per_replica",
     "hmc_dist_hist_device_ptr",
     "hmc_comm_unique_id", "hmc_comm_create", "hmc_comm_create_from_file", "hmc_comm_destroy",
+    "hmc_comm_wrap_nccl",
     "hmc_comm_rank", "hmc_comm_world", "hmc_comm_nccl_version", "hmc_comm_collectives",
     "hmc_allreduce_counts", "hmc_allreduce_totals", "hmc_allreduce_hist",
     "hmc_comm_allreduce_host_u64", "hmc_comm_bcast_host", "hmc_comm_allreduce_device_u64",

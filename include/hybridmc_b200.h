@@ -400,6 +400,8 @@ int hmc_comm_create(const uint8_t id[HMC_COMM_ID_BYTES], int rank, int world, in
  * `path` must not exist when the ranks start (a leftover of a crashed launch would be read
  * as this launch's id): use a fresh name per launch. */
 int hmc_comm_create_from_file(const char *path, int rank, int world, int device, hmc_comm *out);
+/* adopt an ncclComm_t the host already owns (it stays the host's; same libnccl.so.2) */
+int hmc_comm_wrap_nccl(void *nccl_comm, int rank, int world, int device, hmc_comm *out);
 int hmc_comm_destroy(hmc_comm c);
 int hmc_comm_rank(hmc_comm c);
 int hmc_comm_world(hmc_comm c);

@@ -199,3 +199,15 @@ def test_state_entropies_match_avg_s_bias_semantics():
     d = {("01", "11"): 2.0, ("10", "11"): 3.0, ("00", "01"): 4.0, ("00", "10"): 3.5}
     S = state_entropies(2, d)
     assert S == {"11": 0.0, "01": 2.0, "10": 3.0, "00": (6.0 + 6.5) / 2}
+
+
+def test_comm_argument_validation():
+    """the communicator entry points refuse bad arguments before touching NCCL or CUDA"""
+    lib = _lib()
+    c = C.c_void_p()
+    assert lib.hmc_comm_wrap_nccl(None, 0, 1, 0, C.byref(c)) == -1
+    assert lib.hmc_comm_create(None, 0, 1, 0, C.byref(c)) == -1
+    buf = (C.c_uint8 * 128)()
+    assert lib.hmc_comm_create(buf, 3, 2, 0, C.byref(c)) == -1  # rank >= world
+    assert lib.hmc_comm_world(None) == 1 and lib.hmc_comm_rank(None) == 0
+    assert lib.hmc_allreduce_counts(None, None) != 0            # null handle
