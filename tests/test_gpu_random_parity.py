@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from common import OracleRun, first_trace_mismatch, load_config, transition_params
-from hybridmc_b200.engine import PHASE_EQ, PHASE_MAIN, Engine
+from hybridmc_b200.engine import PHASE_MAIN, Engine
 from hybridmc_b200.params import params_from_json, transition_jsons
 
 pytestmark = pytest.mark.gpu
