@@ -317,6 +317,9 @@ void usage() {
                "ensemble mode (the production path; without --replicas: one replica fed the\n"
                "reference's std::mt19937 stream, bit-identical to the reference):\n"
                "  --replicas arg        replicas of the transition on this GPU, pooled counts\n"
+               "                        (or HYBRIDMC_REPLICAS in the environment, for drivers that\n"
+               "                        cannot pass options; likewise HYBRIDMC_ITERS_PER_ROUND,\n"
+               "                        HYBRIDMC_HIST_BINS)\n"
                "  --iters-per-round arg iterations per replica and G-test round\n"
                "                        (default total_iter / replicas, rounded up)\n"
                "  --eq-iters arg        equilibration iterations (default min(total_iter_eq, 8))\n"
@@ -456,6 +459,15 @@ int main(int argc, char *argv[]) {
       pos_ptr = pos_in.data();
     }
 
+    // The unchanged campaign driver passes only `json output [--input-file]`
+    // (tools/init_json.py:149-159): the environment selects the production mode there.
+    auto env_uint = [](const char *name, unsigned &v) {
+      if (v == 0)
+        if (const char *e = std::getenv(name)) v = unsigned(std::atoi(e));
+    };
+    env_uint("HYBRIDMC_REPLICAS", replicas);
+    env_uint("HYBRIDMC_ITERS_PER_ROUND", iters_per_round);
+    env_uint("HYBRIDMC_HIST_BINS", hist_bins);
     if (replicas > 0) {
       // ---- ensemble mode: hmc_run_program_ensemble for this one transition ----
       int rank = 0, world = 1;

@@ -265,6 +265,22 @@ def test_executable_ensemble_mode(tmp_path):
         assert len(f["config"]["int"]) > 0
 
 
+def test_executable_ensemble_mode_from_the_environment(tmp_path):
+    """the unchanged tools/init_json.py passes only `json output` (init_json.py:149-159):
+    HYBRIDMC_REPLICAS in the environment selects the production mode for it"""
+    from hybridmc_b200.output import File
+    jpath, opath = str(tmp_path / "t.json"), str(tmp_path / "t.h5")
+    with open(jpath, "w") as f:
+        json.dump(load_config("8bead_1bond"), f)
+    r = subprocess.run([_exe(), jpath, opath], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, HYBRIDMC_REPLICAS="192", HYBRIDMC_ITERS_PER_ROUND="4",
+                                HYBRIDMC_HIST_BINS="256"))
+    assert r.returncode == 0, r.stderr
+    assert "ensemble of 192 x 1 replicas" in r.stderr
+    with File(opath) as f:
+        assert abs(float(f["s_bias"][0]) - 3.6) < 0.4 and f["dist_hist"].shape == (1, 2, 256)
+
+
 def test_concurrent_executables_share_one_gpu(tmp_path):
     """tools/init_json.py --nproc N starts N executables at once (multiprocessing pool,
     init_json.py:14-36): several `hybridmc --replicas` processes on ONE GPU must all finish
