@@ -265,6 +265,21 @@ def test_executable_ensemble_mode(tmp_path):
         assert len(f["config"]["int"]) > 0
 
 
+def test_get_error_s_bias_tool(tmp_path, monkeypatch):
+    """tools/get_error_s_bias.py's arguments and csv row, the nboot programs being the replicas
+    of one independent-mode launch"""
+    import csv
+    from hybridmc_b200 import get_error_s_bias
+    jpath = str(tmp_path / "hybridmc_0_0_1.json")
+    with open(jpath, "w") as f:
+        json.dump(load_config("8bead_1bond", total_iter=60, total_iter_eq=15, max_g_test_count=4), f)
+    monkeypatch.chdir(tmp_path)
+    mean, var, percent = get_error_s_bias.main([jpath, "48"])
+    row = [float(x) for x in next(csv.reader(open(tmp_path / "hybridmc_0_0_1_s_bias_error.csv")))]
+    assert row == [mean, var, percent]
+    assert 3.0 < mean < 4.5 and 0.0 < var < 0.5 and percent == var / mean * 100
+
+
 def test_executable_ensemble_mode_from_the_environment(tmp_path):
     """the unchanged tools/init_json.py passes only `json output` (init_json.py:149-159):
     HYBRIDMC_REPLICAS in the environment selects the production mode for it"""
