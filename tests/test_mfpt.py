@@ -107,3 +107,44 @@ def test_histogram_bootstrap_variance_matches_repeated_sampling():
     assert boot > 0
     ratio = boot / (2 * np.var(vals, ddof=1))
     assert 0.2 < ratio < 5.0, ratio
+
+
+def test_run_mfpt_collects_a_campaign_directory(tmp_path):
+    """python -m hybridmc_b200.run_mfpt DIR (tools/run_mfpt.py + tools/print_mfpt_to_file.py): one
+    row per hybridmc_<layer>_<bits_i>_<bits_j>.{json,h5} pair, published header, layers ascending"""
+    import csv
+    import json
+
+    from common import load_config
+    from hybridmc_b200 import output, run_mfpt
+    from hybridmc_b200.params import transition_jsons
+    rng = np.random.default_rng(9)
+    master = load_config("test")
+    rmax, nbins = 15.0, 2048
+    picked = [t for t in transition_jsons(master) if t[0] in (0, 1)][:4]
+    expect = {}
+    for layer, bits_in, bits_out, d in picked:
+        fmt = lambda b: "".join("1" if x else "0" for x in b)  # noqa: E731
+        name = "hybridmc_%d_%s_%s" % (layer, fmt(bits_in), fmt(bits_out))
+        nl = sorted(sorted(b) for b in d["nonlocal_bonds"])
+        col = nl.index(sorted(d["transient_bonds"][0]))
+        hist = np.zeros((len(nl), 2, nbins), np.uint64)
+        inner = rng.uniform(d["rh"], d["rc"], 30000)
+        outer = d["rc"] + rng.gamma(2.0, 0.7 + 0.1 * layer, 30000)
+        outer = outer[outer < rmax]
+        hist[col, 1] = np.histogram(inner, bins=nbins, range=(0, rmax))[0]
+        hist[col, 0] = np.histogram(outer, bins=nbins, range=(0, rmax))[0]
+        (tmp_path / (name + ".json")).write_text(json.dumps(d))
+        output.write_hdf5(str(tmp_path / (name + ".h5")), {"dist_hist": hist},
+                          {"dist_hist_rmax": np.float64(rmax)})
+        expect[(fmt(bits_in), fmt(bits_out))] = (
+            layer, mfpt.fpt_from_samples(inner, d["rh"], d["rc"], True),
+            mfpt.fpt_from_samples(outer, d["rc"], outer.max(), False))
+    run_mfpt.main([str(tmp_path), "--procs", "2"])
+    rows = list(csv.reader(open(tmp_path / "mfpt.csv")))
+    assert rows[0] == ["state i bits", "state j bits", "layer", "inner fpt", "outer fpt"]
+    assert len(rows) == 5 and [int(r[2]) for r in rows[1:]] == sorted(int(r[2]) for r in rows[1:])
+    for bi, bo, layer, inner, outer in rows[1:]:
+        e = expect[(bi, bo)]
+        assert int(layer) == e[0]
+        assert float(inner) == pytest.approx(e[1], rel=0.02) and float(outer) == pytest.approx(e[2], rel=0.03)
