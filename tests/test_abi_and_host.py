@@ -211,3 +211,18 @@ def test_comm_argument_validation():
     assert lib.hmc_comm_create(buf, 3, 2, 0, C.byref(c)) == -1  # rank >= world
     assert lib.hmc_comm_world(None) == 1 and lib.hmc_comm_rank(None) == 0
     assert lib.hmc_allreduce_counts(None, None) != 0            # null handle
+
+
+def test_ensemble_program_fails_loudly_without_gpu():
+    """the production entry point through its ctypes mirror (structs, callbacks): without a
+    CUDA device it reports the library's message instead of falling back or crashing"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    _lib()
+    p = params_from_json(load_config("8bead_1bond"))
+    with pytest.raises(eng.EnsembleError) as ei:
+        eng.run_program_ensemble([p], [eng.init_pos_chain(p)], 4, hist_bins=8, hist_rmax=4.0, dist_rows=8)
+    assert "no CPU fallback" in str(ei.value) and ei.value.code < 0
+    with pytest.raises(eng.EngineError):
+        eng.resident_replicas(20)
